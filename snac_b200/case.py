@@ -1,0 +1,75 @@
+"""Case set-up shared by the driver: input files -> decomposition, grids, initial fields.
+
+Mirrors the start-up part of ``program snac`` (reference ``src/main.f90:195-253,413-453,527-561``):
+``read_input`` -> ``initmpi`` -> ``initgrid``/``load_grid`` -> ``distribute_grid``/``bound_grid`` ->
+``initflow``/``initscal`` (or restart files).  Everything here is host-side, O(N) and executed once.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List
+
+import numpy as np
+
+from . import initflow as _if
+from .initgrid import BoxGrid, Grid1D, block_grids, box_grids
+from .initmpi import World, initmpi
+from .param import Params, read_input
+
+
+@dataclasses.dataclass
+class Case:
+    params: Params
+    world: World
+    bgrids: List[List[Grid1D]]
+    grids: List[BoxGrid]
+    rundir: str = "."
+
+
+def setup_case(rundir: str = ".", fft_axis: int = 0, impdiff: bool = False, boussinesq: bool = False,
+               params: Params = None) -> Case:
+    p = params if params is not None else read_input(rundir, fft_axis, impdiff, boussinesq)
+    world = initmpi(p)
+    bg = block_grids(p, rundir)
+    g = box_grids(p, world, bg)
+    return Case(params=p, world=world, bgrids=bg, grids=g, rundir=rundir)
+
+
+def initial_fields(case: Case, ranks=None, noise: bool = False):
+    """Initial u,v,w,p (+scalars) for the given ranks (default: all), ghosted Fortran-order arrays.
+
+    ``set_mean`` (reference src/initflow.f90:288-316) needs a sum over the boxes of a block, so the
+    local means of *all* boxes of the block are evaluated here even when only some ranks are
+    requested (cheap: one pass)."""
+    p, world = case.params, case.world
+    ranks = list(range(world.nrank)) if ranks is None else list(ranks)
+    out = {}
+    need_blocks = {world.boxes[r].block for r in ranks}
+    fields = {}
+    for box in world.boxes:
+        if box.block not in need_blocks:
+            continue
+        b = p.blocks[box.block]
+        l = b.lmax - b.lmin
+        g = case.grids[box.rank]
+        fields[box.rank] = _if.initflow(b.inivel, False, box, g, l, b.bcvel, p.visc, p.bforce[0],
+                                        add_noise_to=noise)
+    for ib in need_blocks:
+        members = [bx.rank for bx in world.boxes if bx.block == ib]
+        b = p.blocks[ib]
+        l = b.lmax - b.lmin
+        if fields[members[0]][4]:  # is_mean
+            meanold = sum(_if.set_mean_local(case.grids[r].dxc, case.grids[r].dyf, case.grids[r].dzf, l,
+                                             fields[r][0]) for r in members)
+            if meanold != 0.0:
+                for r in members:
+                    fields[r][0][...] = fields[r][0] / meanold * fields[r][5]
+    for r in ranks:
+        box = world.boxes[r]
+        b = p.blocks[box.block]
+        l = b.lmax - b.lmin
+        u, v, w, pr = fields[r][:4]
+        s = [_if.initscal(p.iniscal[i], b.bcscal[:, :, i], box, case.grids[r], l, bool(p.is_sforced[i]),
+                          float(p.scalf[i])) for i in range(p.nscal)]
+        out[r] = dict(u=u, v=v, w=w, p=pr, s=s)
+    return out
