@@ -1,0 +1,164 @@
+/* snac_b200.h -- C ABI of the B200-native pressure-correction pipeline of SNaC.
+ *
+ * Drop-in boundary: the body of the RK3 sub-step loop of the reference driver
+ * (reference src/main.f90:906-1033) plus its one-time set-up calls (src/main.f90:726-886).
+ * The reference binds its native dependencies with ISO_C_BINDING `bind(C)` interfaces
+ * (src/fftw.f90:9-28); this header is what a `bind(C)` interface module for the GPU path would
+ * mirror.  Everything is `extern "C"`, plain pointers and sizes.
+ *
+ * Conventions
+ *   - "box" = what the reference calls an MPI rank: one Cartesian sub-box `lo:hi` of one block
+ *     (src/initmpi.f90:117-132).  A process (one per GPU) may own several boxes.
+ *   - small index arrays are C-ordered: [idir][ib] with idir = 0,1,2 (x,y,z) and ib = 0 (lower
+ *     face), 1 (upper face); the Fortran arrays are (0:1,1:3), i.e. the transpose.
+ *   - host field arrays are laid out exactly like the reference's allocations
+ *     `u(lo(1)-1:hi(1)+1, lo(2)-1:hi(2)+1, lo(3)-1:hi(3)+1)` (src/main.f90:226-231): column-major,
+ *     one ghost layer, the pointer addresses element (lo-1,lo-1,lo-1).
+ *   - every entry point returns 0 on success and a negative value on error;
+ *     `snac_last_error` returns the message.  There is no CPU fallback: without a CUDA device
+ *     `snac_create` fails.
+ */
+#ifndef SNAC_B200_H
+#define SNAC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNAC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SNAC_API __attribute__((visibility("default")))
+#else
+#define SNAC_API
+#endif
+
+typedef struct snac_handle snac_handle;
+
+/* field identifiers for upload/download/boundp */
+enum {
+  SNAC_FIELD_U = 0,   /* u(lo-1:hi+1,...)  src/main.f90:226 */
+  SNAC_FIELD_V = 1,
+  SNAC_FIELD_W = 2,
+  SNAC_FIELD_P = 3,   /* pressure p */
+  SNAC_FIELD_PP = 4,  /* pressure correction pp in physical space (after the backward transform) */
+  SNAC_FIELD_RHS = 5, /* Poisson right-hand side: the reference's pp between fillps and the solve */
+  SNAC_FIELD_PO = 6,  /* solver iterate / initial guess po (src/main.f90:1010,1022) */
+  SNAC_FIELD_DUDTRKO = 7,
+  SNAC_FIELD_DVDTRKO = 8,
+  SNAC_FIELD_DWDTRKO = 9,
+  SNAC_FIELD_S0 = 16,      /* scalar i  = SNAC_FIELD_S0 + i        */
+  SNAC_FIELD_DSDTRKO0 = 32 /* its RK history = SNAC_FIELD_DSDTRKO0 + i */
+};
+
+#define SNAC_MAX_SCAL 8
+
+/* Global (per run) parameters: what the hot path reads from mod_param (src/param.f90:23-45,
+ * 88-106) plus the reference's compile-time switches (configs/defaults/build-default.conf:12-19)
+ * turned into run-time values. */
+typedef struct snac_params {
+  int abi_version;        /* SNAC_ABI_VERSION */
+  int device;             /* CUDA device ordinal of this process */
+  int nrank;              /* number of boxes in the run (reference: MPI_COMM_WORLD size) */
+  int nproc;              /* number of processes (GPUs) */
+  int myproc;             /* this process */
+  const int *rank_owner;  /* [nrank] process owning each box (NULL: all owned by process 0) */
+  int periods[3];         /* global extent in periodic directions, else 0 (src/initmpi.f90:107-113) */
+  int fft_axis;           /* 0: 3-D solve; 1,2,3: transforms along x,y,z (FFT_AXIS build option) */
+  int impdiff;            /* IMPDIFF build option */
+  int boussinesq;         /* BOUSSINESQ_BUOYANCY build option */
+  int nscal;
+  double visc;            /* 1/visci (src/param.f90:175) */
+  double bforce[3];
+  double gacc[3];
+  double beta;
+  double vol_all;         /* src/param.f90:239-240 */
+  double alphai[SNAC_MAX_SCAL];   /* scalar inverse diffusivities (&scalar) */
+  double ssource[SNAC_MAX_SCAL];
+  int is_sforced[SNAC_MAX_SCAL];
+  double scalf[SNAC_MAX_SCAL];
+  double hypre_tol;       /* relative residual tolerance of the linear solves (src/param.f90:15-17) */
+  int hypre_maxiter;
+  int hypre_solver_i;     /* accepted for compatibility; the solver is always geometric multigrid */
+  /* multigrid tuning (0 = default) */
+  int mg_npre, mg_npost, mg_nbottom;
+} snac_params;
+
+/* Per-box description: the outputs of initmpi / initgrid / read_input that the hot path uses
+ * (src/initmpi.f90:9-10, src/initgrid.f90:49-127, src/param.f90:46-57). */
+typedef struct snac_box {
+  int rank;               /* 0-based box id (reference myid) */
+  int block;              /* 0-based block id */
+  int lo[3], hi[3];       /* global indices, 1-based like the reference */
+  int nb[3][2];           /* neighbour box id or -1 (MPI_PROC_NULL) */
+  int is_bound[3][2];
+  char cbcvel[3][3][2];   /* [ivel][idir][ib] : 'D','N','F' (block_cbcvel(ib,idir,ivel)) */
+  double bcvel[3][3][2];
+  char cbcpre[3][2];
+  double bcpre[3][2];
+  char cbcscal[SNAC_MAX_SCAL][3][2];
+  double bcscal[SNAC_MAX_SCAL][3][2];
+  /* 1-D metric arrays, each of length n+2 (index lo-1..hi+1), AFTER bound_grid */
+  const double *dxc, *dxf, *dyc, *dyf, *dzc, *dzf;
+  double dl[3][2];        /* d?c_g(lo_g-1), d?c_g(hi_g)  (src/main.f90:726-728) */
+  double dlf[3][2];       /* d?f_g(lo_g),   d?f_g(hi_g)  (src/main.f90:771-773; IMPDIFF) */
+} snac_box;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+SNAC_API int snac_create(const snac_params *params, snac_handle **out);
+SNAC_API int snac_add_box(snac_handle *h, const snac_box *box);
+/* Builds device state for all added boxes: fields, boundary/halo tables, transform plans
+ * (fftini, src/fft.f90:10-69), boundary RHS (init_bc_rhs, src/solver.f90:44-157), multigrid
+ * hierarchies (replacing init_matrix_3d, init_matrix_2d, create_solver and setup_solver,
+ * src/solver.f90:158-484). */
+SNAC_API int snac_commit(snac_handle *h);
+SNAC_API int snac_finalize(snac_handle *h);
+SNAC_API const char *snac_last_error(const snac_handle *h);   /* h may be NULL: error of snac_create */
+
+/* ---- field transfer (host layout: see header comment) ------------------------------------ */
+SNAC_API int snac_upload(snac_handle *h, int rank, int field, const double *host);
+SNAC_API int snac_download(snac_handle *h, int rank, int field, double *host);
+
+/* ---- fine-grained entry points, 1:1 with the reference subroutines -------------------------
+ * Each acts on all boxes owned by the process. */
+SNAC_API int snac_rk_mom(snac_handle *h, int irk, double dt);            /* rk_mom, src/rk.f90:7-128; irk=1..3 */
+SNAC_API int snac_rk_scal(snac_handle *h, int irk, double dt, int iscal);/* rk_scal + bulk_forcing_s, src/rk.f90:130-204 */
+SNAC_API int snac_bounduvw(snac_handle *h, int is_correc);               /* bounduvw, src/bound.f90:8-66 */
+SNAC_API int snac_boundp(snac_handle *h, int field);                     /* boundp, src/bound.f90:68-106 */
+SNAC_API int snac_fillps(snac_handle *h, double dtrk);                   /* fillps, src/fillps.f90:7-54 -> RHS */
+SNAC_API int snac_updt_rhs(snac_handle *h);                              /* updt_rhs, src/bound.f90:543-585 on RHS */
+SNAC_API int snac_fft(snac_handle *h, int dir);  /* fft, src/fft.f90:85-94: dir=+1 RHS in place; dir=-1 PO -> PP, times normfft (src/main.f90:1017-1020) */
+SNAC_API int snac_solve_n_helmholtz_2d(snac_handle *h);                  /* src/solver.f90:843-922: RHS,PO -> PO */
+SNAC_API int snac_solve_helmholtz(snac_handle *h);                       /* src/solver.f90:524-573: RHS,PO -> PO (=PP) */
+SNAC_API int snac_correc(snac_handle *h, double dtrk);                   /* correc, src/correc.f90:7-48 */
+SNAC_API int snac_updt_pressure(snac_handle *h, double alpha);           /* updt_pressure, src/updt_pressure.f90:7-47 */
+SNAC_API int snac_chkdt(snac_handle *h, double *dt_cfl);                 /* chkdt, src/chkdt.f90:8-56 (global) */
+SNAC_API int snac_chkdiv(snac_handle *h, double *divtot, double *divmax);/* chkdiv, src/chkdiv.f90:8-44 (global) */
+
+/* ---- coarse-grained entry point: the whole `do irk=1,3` body, src/main.f90:906-1033 -------- */
+SNAC_API int snac_step(snac_handle *h, double dt);
+
+/* ---- diagnostics ------------------------------------------------------------------------- */
+/* iterations and worst relative residual of the most recent linear solve (the reference ignores
+ * HYPRE's ierr and iteration counts, src/solver.f90:553-556; non-convergence is not an error). */
+SNAC_API int snac_solver_stats(snac_handle *h, int *iters, double *relres);
+/* Per-kernel-class device timing.  While enabled, every class section is bracketed by CUDA events
+ * on the handle's stream and waited for, so the stream is serialised: use it to attribute time, not
+ * to measure throughput.  Classes are numbered from 0; snac_profile_name returns NULL past the end. */
+SNAC_API int snac_profile_enable(snac_handle *h, int on);
+SNAC_API int snac_profile_get(snac_handle *h, int cls, double *ms, long long *launches);
+SNAC_API const char *snac_profile_name(int cls);
+/* CUDA-event stopwatch on the handle's stream (start records, stop records + waits). */
+SNAC_API int snac_timer_start(snac_handle *h);
+SNAC_API int snac_timer_stop(snac_handle *h, double *ms);
+/* number of kernels launched by this handle since creation */
+SNAC_API long long snac_launch_count(const snac_handle *h);
+/* blocks until all device work of the handle is complete */
+SNAC_API int snac_sync(snac_handle *h);
+/* CUDA stream (cudaStream_t) the handle launches on, for event timing by the caller */
+SNAC_API void *snac_stream(snac_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAC_B200_H */

@@ -1,0 +1,114 @@
+// K2: halo exchange and boundary-condition face fills as packed device kernels.
+//
+// Replaces updthalo (reference src/bound.f90:587-650: two blocking MPI_SENDRECV per direction and
+// field with derived vector types, src/initmpi.f90:255-271) and set_bc (src/bound.f90:108-248).
+// All boxes and all fields of one bounduvw/boundp call are handled by ONE launch per direction:
+// a table of plane-copy descriptors (halos between boxes resident on this GPU, including periodic
+// self-neighbours) and a table of face-fill descriptors live in device memory, built at commit.
+// Directions are processed x, y, z with full ghost extents so that edges and corners propagate
+// exactly as in the reference (src/bound.f90:26-34).
+#include "common.h"
+
+namespace snac {
+
+__global__ void copy_ops_kernel(const CopyOp *ops) {
+  const CopyOp op = ops[blockIdx.y];
+  const long tot = (long)op.na * op.nb;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+    const int ia = (int)(t % op.na), ib = (int)(t / op.na);
+    op.dst[ia * op.dsa + ib * op.dsb] = op.src[ia * op.ssa + ib * op.ssb];
+  }
+}
+
+__global__ void face_ops_kernel(const FaceOp *ops) {
+  const FaceOp op = ops[blockIdx.y];
+  const long tot = (long)op.na * op.nb;
+  const long sd = op.sd;
+  const int n = op.n;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+    const int ia = (int)(t % op.na), ib = (int)(t / op.na);
+    double *q = op.p + ia * op.sa + ib * op.sb;
+    switch (op.kind) {   // src/bound.f90:135-246
+      case FACE_CEN_LO: q[0] = op.factor + op.sgn * q[sd]; break;
+      case FACE_CEN_HI: q[(n + 1) * sd] = op.factor + op.sgn * q[n * sd]; break;
+      case FACE_STAG_D_LO: q[0] = op.factor; break;
+      case FACE_STAG_D_HI: q[n * sd] = op.factor; q[(n + 1) * sd] = q[(n - 1) * sd]; break;
+      case FACE_STAG_N_LO: q[0] = op.factor + q[sd]; break;
+      case FACE_STAG_N_HI: {
+        const double v = op.factor + q[(n - 1) * sd];
+        q[n * sd] = v;
+        q[(n + 1) * sd] = v;
+      } break;
+    }
+  }
+}
+
+template <class T>
+static int max_plane(const std::vector<T> &v) {
+  long m = 1;
+  for (auto &o : v) m = std::max(m, (long)o.na * o.nb);
+  return (int)std::min<long>((m + 255) / 256, 256);
+}
+
+struct OpsMeta { int gx; };
+
+void launch_copy_ops(Ctx &ctx, const DevOps<CopyOp> &ops) {
+  if (!ops.count) return;
+  dim3 grd(ops.count ? 64 : 1, ops.count);
+  copy_ops_kernel<<<grd, 256, 0, ctx.stream>>>(ops.d);
+  ctx.launches++;
+}
+
+void launch_face_ops(Ctx &ctx, const DevOps<FaceOp> &ops) {
+  if (!ops.count) return;
+  dim3 grd(64, ops.count);
+  face_ops_kernel<<<grd, 256, 0, ctx.stream>>>(ops.d);
+  ctx.launches++;
+}
+
+void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields) {
+  // `fields` holds, for each exchanged array, one entry per local box, grouped:
+  // fields[f*nlocal + lb].  Ghost plane of box lb on side ib comes from the neighbour's first/last
+  // interior plane (src/bound.f90:602-607).
+  const int nl = (int)ctx.boxes.size();
+  if (fields.size() % nl) throw Error("Exchange::build: field list is not a multiple of the box count");
+  std::vector<CopyOp> ops[3];
+  for (size_t f = 0; f < fields.size() / nl; ++f) {
+    for (int lb = 0; lb < nl; ++lb) {
+      const ExField &me = fields[f * nl + lb];
+      const snac_box &info = ctx.boxes[lb]->info;
+      for (int d = 0; d < 3; ++d) {
+        const int a = (d + 1) % 3, b = (d + 2) % 3;
+        const int da = std::min(a, b), db = std::max(a, b);  // keep x (or y) fastest in the plane
+        for (int ib = 0; ib < 2; ++ib) {
+          const int nbr = info.nb[d][ib];
+          if (nbr < 0) continue;
+          const int ln = ctx.local_of_rank[nbr];
+          if (ln < 0) throw Error("halo exchange with a box owned by another process is not available in this build");
+          const ExField &src = fields[f * nl + ln];
+          if (src.g.n[da] != me.g.n[da] || src.g.n[db] != me.g.n[db])
+            throw Error("halo exchange: neighbouring boxes are not face-congruent");
+          CopyOp op;
+          op.na = me.g.n[da] + 2;
+          op.nb = me.g.n[db] + 2;
+          op.ssa = src.g.st(da); op.ssb = src.g.st(db);
+          op.dsa = me.g.st(da);  op.dsb = me.g.st(db);
+          const long sidx = (ib == 0) ? src.g.n[d] : 1;          // neighbour's hi / lo interior plane
+          const long didx = (ib == 0) ? 0 : me.g.n[d] + 1;        // my lo / hi ghost plane
+          op.src = src.p + sidx * src.g.st(d);
+          op.dst = me.p + didx * me.g.st(d);
+          ops[d].push_back(op);
+        }
+      }
+    }
+  }
+  for (int d = 0; d < 3; ++d) local[d].upload(ops[d]);
+}
+
+void Exchange::run(Ctx &ctx, int dir) const { launch_copy_ops(ctx, local[dir]); }
+
+void FaceFill::run(Ctx &ctx) const {
+  for (int d = 0; d < 3; ++d) launch_face_ops(ctx, ops[d]);
+}
+
+}  // namespace snac

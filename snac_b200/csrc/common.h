@@ -1,0 +1,335 @@
+// Internal declarations shared by the CUDA translation units of libsnacb200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/snac_b200.h"
+
+namespace snac {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define SNAC_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      throw ::snac::Error(std::string(#expr) + " failed: " + cudaGetErrorString(e_) + " at " +   \
+                          __FILE__ + ":" + std::to_string(__LINE__));                            \
+  } while (0)
+
+inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
+
+// Ghosted 3-D array in device memory, x fastest.  Element (i,j,k), i in [0,n1+1] (Fortran index
+// lo-1+i), lives at p[i + sy*j + sz*k].  The allocation is padded so that the first interior
+// element of every row, (1,j,k), is 128-byte aligned and sy is a multiple of 16 doubles.
+struct Grid3 {
+  int n[3] = {0, 0, 0};  // interior sizes
+  long sy = 0, sz = 0;
+  long alloc_elems() const { return 16 + sz * (n[2] + 2); }
+  long st(int d) const { return d == 0 ? 1 : (d == 1 ? sy : sz); }
+  static Grid3 make(int n1, int n2, int n3) {
+    Grid3 g;
+    g.n[0] = n1; g.n[1] = n2; g.n[2] = n3;
+    g.sy = round_up(n1 + 2, 16);
+    g.sz = g.sy * (n2 + 2);
+    return g;
+  }
+};
+
+// Owning device buffer of doubles (zero-initialised).
+struct DevBuf {
+  double *raw = nullptr;
+  size_t elems = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : raw(o.raw), elems(o.elems) { o.raw = nullptr; o.elems = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); raw = o.raw; elems = o.elems; o.raw = nullptr; o.elems = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    elems = n;
+    if (n) {
+      SNAC_CUDA(cudaMalloc(&raw, n * sizeof(double)));
+      SNAC_CUDA(cudaMemset(raw, 0, n * sizeof(double)));
+    }
+  }
+  void release() {
+    if (raw) cudaFree(raw);
+    raw = nullptr;
+    elems = 0;
+  }
+};
+
+// A field = buffer + pointer to its (0,0,0) ghost corner.
+struct Field3 {
+  DevBuf buf;
+  double *p = nullptr;  // element (0,0,0)
+  void alloc(const Grid3 &g) {
+    buf.alloc(g.alloc_elems());
+    p = buf.raw + 15;  // so that (1,0,0) is 128-byte aligned
+  }
+};
+
+// 1-D device array uploaded from host.
+struct Dev1 {
+  DevBuf buf;
+  const double *p() const { return buf.raw; }
+  void upload(const std::vector<double> &h) {
+    buf.alloc(h.size());
+    if (!h.empty())
+      SNAC_CUDA(cudaMemcpy(buf.raw, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// halo copies and boundary-condition face fills (bound.cu)
+// ------------------------------------------------------------------------------------------
+struct CopyOp {  // dst plane <- src plane, both 2-D with extents (na, nb)
+  const double *src;
+  double *dst;
+  long ssa, ssb, dsa, dsb;
+  int na, nb;
+};
+
+enum FaceKind : int {
+  FACE_CEN_LO = 0,   // q(0)   = factor + sgn*q(1)
+  FACE_CEN_HI = 1,   // q(n+1) = factor + sgn*q(n)
+  FACE_STAG_D_LO = 2,  // q(0) = factor
+  FACE_STAG_D_HI = 3,  // q(n) = factor ; q(n+1) = q(n-1)
+  FACE_STAG_N_LO = 4,  // q(0) = factor + q(1)
+  FACE_STAG_N_HI = 5   // q(n) = factor + q(n-1) ; q(n+1) = q(n)
+};
+
+struct FaceOp {
+  double *p;      // (0,0,0) corner of the field
+  long sd, sa, sb;  // strides: normal, and the two in-plane directions
+  int n, na, nb;  // interior size along the normal; in-plane extents (full ghost extents)
+  int kind;
+  double factor, sgn;
+};
+
+template <class T>
+struct DevOps {  // device-resident array of ops
+  T *d = nullptr;
+  int count = 0;
+  void upload(const std::vector<T> &h) {
+    if (d) cudaFree(d);
+    d = nullptr;
+    count = (int)h.size();
+    if (count) {
+      SNAC_CUDA(cudaMalloc(&d, count * sizeof(T)));
+      SNAC_CUDA(cudaMemcpy(d, h.data(), count * sizeof(T), cudaMemcpyHostToDevice));
+    }
+  }
+  ~DevOps() { if (d) cudaFree(d); }
+  DevOps() = default;
+  DevOps(const DevOps &) = delete;
+  DevOps &operator=(const DevOps &) = delete;
+};
+
+struct Ctx;
+
+// One ghosted array per local box taking part in an exchange.
+struct ExField {
+  int box;       // local box index
+  double *p;     // (0,0,0) corner
+  Grid3 g;
+};
+
+// Halo exchange of a group of fields (all local boxes), one direction at a time
+// (updthalo, reference src/bound.f90:587-650).
+struct Exchange {
+  DevOps<CopyOp> local[3];
+  void build(Ctx &ctx, const std::vector<ExField> &fields);
+  void run(Ctx &ctx, int dir) const;      // one direction
+  void run_all(Ctx &ctx) const {          // x, then y, then z (edges/corners propagate)
+    for (int d = 0; d < 3; ++d) run(ctx, d);
+  }
+};
+
+struct FaceFill {
+  DevOps<FaceOp> ops[3];
+  void upload(const std::vector<FaceOp> (&h)[3]) { for (int d = 0; d < 3; ++d) ops[d].upload(h[d]); }
+  void run(Ctx &ctx) const;
+};
+
+void launch_copy_ops(Ctx &ctx, const DevOps<CopyOp> &ops);
+void launch_face_ops(Ctx &ctx, const DevOps<FaceOp> &ops);
+
+// ------------------------------------------------------------------------------------------
+// geometry passed by value to the stencil kernels
+// ------------------------------------------------------------------------------------------
+struct BoxGeom {
+  int n[3];
+  long sy, sz;
+  // ghosted 1-D metric arrays (index 0..n+1) and their reciprocals
+  const double *dc[3], *df[3], *rdc[3], *rdf[3];
+};
+
+// ------------------------------------------------------------------------------------------
+// transforms (fft.cu)
+// ------------------------------------------------------------------------------------------
+enum R2RKind : int {  // names follow the FFTW r2r kinds the reference selects (src/fft.f90:96-149)
+  K_R2HC = 0, K_HC2R = 1, K_DHT = 2, K_REDFT00 = 3, K_REDFT01 = 4, K_REDFT10 = 5, K_REDFT11 = 6,
+  K_RODFT00 = 7, K_RODFT01 = 8, K_RODFT10 = 9, K_RODFT11 = 10
+};
+
+struct R2RPlan {
+  int n = 0;       // box size along the axis
+  int nt = 0;      // transform length (n - q)
+  int axis = 0;
+  int kind_fwd = 0, kind_bwd = 0;
+  double normfft = 1.0;
+  Dev1 mat_fwd, mat_bwd;  // dense nt x nt matrices (row-major [k][j]) for the generic path
+  Dev1 twiddle;           // cos/sin tables of the fast path
+  bool fast = false;
+};
+
+void find_fft(const char bc[2], bool centered, int &kf, int &kb, double norm[2]);
+void r2r_plan_init(R2RPlan &pl, int axis, int n, const char bc[2], bool centered);
+std::vector<double> r2r_eigenvalues(int n, const char bc[2], bool centered);
+// in -> out along plan.axis over the interior of a ghosted box (in == out allowed); out *= scale
+void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const Grid3 &g, const double *in, double *out,
+                 double scale);
+
+// ------------------------------------------------------------------------------------------
+// multigrid (mg.cu)
+// ------------------------------------------------------------------------------------------
+struct MGLevelBox {
+  Grid3 g;
+  Field3 x, b;                 // x is owned except on level 0 where it may alias a context field
+  double *xp = nullptr, *bp = nullptr;
+  Dev1 am[3], ap[3], ad[3], w[3];   // ghosted 1-D coefficient arrays (index 0..n+1)
+  std::vector<double> h_w[3];       // host copy of cell widths (for coarsening)
+};
+
+struct MGKernelBox {  // by-value kernel argument
+  int n[3];
+  long sy, sz;
+  double *x;
+  double *b;
+  const double *am[3], *ap[3], *ad[3], *w[3];
+  const double *lam;  // per-index eigenvalue along the uncoupled axis (or nullptr)
+  int coupled[3];
+  int fft_dir;        // -1 or the uncoupled direction
+};
+
+struct MGLevel {
+  std::vector<MGLevelBox> boxes;   // one per local box
+  Exchange ex;                     // halo exchange of x on this level
+  int coarsen[3] = {0, 0, 0};      // directions coarsened going to the next level
+};
+
+struct MGSolver {
+  int fft_dir = -1;                // uncoupled direction (fft_axis-1) or -1
+  bool centered[3] = {true, true, true};
+  std::vector<std::unique_ptr<MGLevel>> levels;
+  std::vector<Dev1> lam;           // per local box (ghosted along the fft axis), (lambda)/dl^2
+  int nq = 1;                      // number of independent planes (wavenumbers)
+  DevBuf norms;                    // [2*nq]: sum r^2, sum b^2 per plane
+  std::vector<double> h_norms;
+  int last_iters = 0;
+  double last_relres = 0.0;
+  double alpha = 0.0;              // extra diagonal shift (IMPDIFF: alphai)
+  void setup(Ctx &ctx, const bool centered_[3]);
+  void solve(Ctx &ctx);
+};
+
+// ------------------------------------------------------------------------------------------
+// per-box state
+// ------------------------------------------------------------------------------------------
+struct Box {
+  snac_box info;
+  Grid3 g;
+  std::vector<double> h_dc[3], h_df[3];
+  Dev1 dc[3], df[3], rdc[3], rdf[3];
+  Field3 u[2], v[2], w[2];  // double-buffered velocity (rk_mom writes the other parity)
+  Field3 p, pp, rhs, po;
+  Field3 du, dv, dw;        // d?dtrko
+  Field3 s[SNAC_MAX_SCAL], ds[SNAC_MAX_SCAL];
+  // Poisson RHS: weights (cell width, or 1 along the transform axis), 1/width along the transform
+  // axis (else 1), and the boundary coefficient of init_bc_rhs per face
+  Dev1 wq[3], gq[3];
+  double cbp[3][2];
+  bool pp_is_po = false;    // 3-D solve: pp aliases the solver iterate
+  double *pp_ptr() const { return pp_is_po ? po.p : pp.p; }
+  BoxGeom geom() const;
+};
+
+// per-kernel-class device timing (enabled by snac_profile_enable; serialises the stream)
+enum ProfClass : int {
+  PC_RK_MOM = 0, PC_HALO_BC, PC_FILLPS, PC_FFT_FWD, PC_MG_SMOOTH0, PC_MG_RESTRICT0, PC_MG_PROLONG0, PC_MG_COARSE,
+  PC_FFT_BWD, PC_CORREC, PC_CHK, PC_COUNT
+};
+
+struct Ctx {
+  snac_params prm;
+  bool prof_on = false;
+  double prof_ms[PC_COUNT] = {0};
+  long long prof_n[PC_COUNT] = {0};
+  cudaEvent_t prof_ev[2] = {nullptr, nullptr};
+  cudaEvent_t timer_ev[2] = {nullptr, nullptr};
+  std::vector<int> owner;
+  std::vector<std::unique_ptr<Box>> boxes;  // local boxes
+  std::vector<int> local_of_rank;           // rank -> local index or -1
+  cudaStream_t stream = nullptr;
+  bool committed = false;
+  int par = 0;                              // which velocity buffer is current
+  long long launches = 0;
+  std::string err;
+  // exchanges / BC fills
+  Exchange ex_uvw[2], ex_p, ex_pp;
+  FaceFill bc_uvw[2][2];   // [parity][is_correc]
+  FaceFill bc_p, bc_pp;
+  Exchange ex_s[SNAC_MAX_SCAL];
+  FaceFill bc_s[SNAC_MAX_SCAL];
+  // transforms and solvers
+  R2RPlan plan_p;
+  MGSolver psolver;
+  // reductions
+  DevBuf red;               // scratch for chkdt/chkdiv
+  double *h_red = nullptr;  // pinned
+  Box &box_of_rank(int rank);
+};
+
+struct ProfScope {
+  Ctx &c;
+  int cls;
+  long long l0;
+  ProfScope(Ctx &ctx, int cls_) : c(ctx), cls(cls_), l0(ctx.launches) {
+    if (c.prof_on) cudaEventRecord(c.prof_ev[0], c.stream);
+  }
+  ~ProfScope() {
+    if (!c.prof_on) return;
+    cudaEventRecord(c.prof_ev[1], c.stream);
+    cudaEventSynchronize(c.prof_ev[1]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c.prof_ev[0], c.prof_ev[1]);
+    c.prof_ms[cls] += ms;
+    c.prof_n[cls] += c.launches - l0;
+  }
+};
+
+// mom.cu / pois.cu entry points (one call handles one box)
+void launch_rk_mom(Ctx &ctx, Box &b, int irk, double dt);
+void launch_fillps(Ctx &ctx, Box &b, double dtrk);
+void launch_fillps_bc(Ctx &ctx, Box &b, double dtrk);
+void launch_updt_rhs(Ctx &ctx, Box &b);
+void launch_correc_updt(Ctx &ctx, Box &b, double dtrk, double alpha, bool do_correc, bool do_updt);
+void launch_chk(Ctx &ctx, Box &b, double *d_out /* [4]: dti_max, divtot, divmax, - */);
+void compute_bc_rhs(Ctx &ctx, Box &b);
+
+}  // namespace snac
