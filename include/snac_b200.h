@@ -43,10 +43,11 @@ enum {
   SNAC_FIELD_P = 3,   /* pressure p */
   SNAC_FIELD_PP = 4,  /* pressure correction pp in physical space (after the backward transform) */
   SNAC_FIELD_RHS = 5, /* Poisson right-hand side: the reference's pp between fillps and the solve */
-  SNAC_FIELD_PO = 6,  /* solver iterate / initial guess po (src/main.f90:1010,1022) */
+  SNAC_FIELD_PO = 6,  /* solver iterate / initial guess po (src/main.f90:1010,1022); spectral space when fft_axis > 0 */
   SNAC_FIELD_DUDTRKO = 7,
   SNAC_FIELD_DVDTRKO = 8,
   SNAC_FIELD_DWDTRKO = 9,
+  SNAC_FIELD_RHS_HAT = 10, /* transformed right-hand side (index along the transform axis = wavenumber) */
   SNAC_FIELD_S0 = 16,      /* scalar i  = SNAC_FIELD_S0 + i        */
   SNAC_FIELD_DSDTRKO0 = 32 /* its RK history = SNAC_FIELD_DSDTRKO0 + i */
 };
@@ -82,6 +83,7 @@ typedef struct snac_params {
   int hypre_solver_i;     /* accepted for compatibility; the solver is always geometric multigrid */
   /* multigrid tuning (0 = default) */
   int mg_npre, mg_npost, mg_nbottom;
+  int mg_generic;         /* 1: always use the general multi-box multigrid kernels */
 } snac_params;
 
 /* Per-box description: the outputs of initmpi / initgrid / read_input that the hot path uses
@@ -127,7 +129,7 @@ SNAC_API int snac_bounduvw(snac_handle *h, int is_correc);               /* boun
 SNAC_API int snac_boundp(snac_handle *h, int field);                     /* boundp, src/bound.f90:68-106 */
 SNAC_API int snac_fillps(snac_handle *h, double dtrk);                   /* fillps, src/fillps.f90:7-54 -> RHS */
 SNAC_API int snac_updt_rhs(snac_handle *h);                              /* updt_rhs, src/bound.f90:543-585 on RHS */
-SNAC_API int snac_fft(snac_handle *h, int dir);  /* fft, src/fft.f90:85-94: dir=+1 RHS in place; dir=-1 PO -> PP, times normfft (src/main.f90:1017-1020) */
+SNAC_API int snac_fft(snac_handle *h, int dir);  /* fft, src/fft.f90:85-94: dir=+1 RHS -> RHS_HAT; dir=-1 PO -> PP, times normfft (src/main.f90:1017-1020) */
 SNAC_API int snac_solve_n_helmholtz_2d(snac_handle *h);                  /* src/solver.f90:843-922: RHS,PO -> PO */
 SNAC_API int snac_solve_helmholtz(snac_handle *h);                       /* src/solver.f90:524-573: RHS,PO -> PO (=PP) */
 SNAC_API int snac_correc(snac_handle *h, double dtrk);                   /* correc, src/correc.f90:7-48 */

@@ -107,9 +107,10 @@ static void commit(Ctx &ctx) {
       b.wq[d].upload(wq); b.gq[d].upload(gq);
     }
     for (int q = 0; q < 2; ++q) { b.u[q].alloc(b.g); b.v[q].alloc(b.g); b.w[q].alloc(b.g); }
-    b.p.alloc(b.g); b.rhs.alloc(b.g); b.po.alloc(b.g);
+    b.p.alloc(b.g); b.rhs.alloc(b.g);
     b.pp_is_po = (ctx.prm.fft_axis == 0);
-    if (!b.pp_is_po) b.pp.alloc(b.g);
+    if (b.pp_is_po) b.po.alloc(b.g);
+    else { b.pp.alloc(b.g); b.stage.alloc(b.g); }
     b.du.alloc(b.g); b.dv.alloc(b.g); b.dw.alloc(b.g);
     for (int s = 0; s < ctx.prm.nscal; ++s) { b.s[s].alloc(b.g); b.ds[s].alloc(b.g); }
     compute_bc_rhs(ctx, b);
@@ -158,8 +159,48 @@ static void commit(Ctx &ctx) {
         throw Error("all boxes must have the same size and boundary conditions along the transform axis (src/sanity.f90:66-100)");
     r2r_plan_init(ctx.plan_p, fa, b0.g.n[fa], bc, true);
   }
-  const bool cen[3] = {true, true, true};
-  ctx.psolver.setup(ctx, cen);
+  {  // the pressure problem as the solver sees it: canonical (permuted) layout when batched
+    const bool batched = ctx.prm.fft_axis > 0;
+    MGSolver &S = ctx.psolver;
+    if (batched) {
+      int q = 0;
+      for (int d = 0; d < 3; ++d) if (d != fa) S.perm[q++] = d;
+      S.perm[2] = fa;
+    }
+    std::vector<SBox> sb(nl);
+    for (int lb = 0; lb < nl; ++lb) {
+      Box &b = *ctx.boxes[lb];
+      SBox &s = sb[lb];
+      for (int sd = 0; sd < 3; ++sd) {
+        const int d = S.perm[sd];
+        s.n[sd] = b.g.n[d];
+        s.d1[sd] = b.h_dc[d];
+        s.d2[sd] = b.h_df[d];
+        for (int ib = 0; ib < 2; ++ib) {
+          s.nb[sd][ib] = b.info.nb[d][ib];
+          s.phys[sd][ib] = b.info.is_bound[d][ib] && ctx.prm.periods[d] == 0;
+          s.sgn[sd][ib] = 0.0;
+          if (s.phys[sd][ib] && !(batched && sd == 2)) {   // src/solver.f90:71-94 (centred unknowns)
+            const char c = b.info.cbcpre[d][ib];
+            if (c == 'N') s.sgn[sd][ib] = 1.0;
+            else if (c == 'D') s.sgn[sd][ib] = -1.0;
+            else throw Error("pressure boundary condition on a physical face must be 'D' or 'N'");
+          }
+        }
+      }
+      if (batched) {  // eigenvalues / dl^2 (src/fft.f90:151-189, src/solver.f90:1124-1138)
+        const char bc[2] = {b.info.cbcpre[fa][0], b.info.cbcpre[fa][1]};
+        std::vector<double> l = r2r_eigenvalues(b.g.n[fa], bc, true);
+        const double dl = b.info.dl[fa][0];
+        s.lam.assign(l.size() + 2, 0.0);
+        for (size_t k = 0; k < l.size(); ++k) s.lam[k + 1] = l[k] / (dl * dl);
+      } else {
+        s.x = b.po.p;
+        s.b = b.rhs.p;
+      }
+    }
+    S.setup(ctx, std::move(sb), batched);
+  }
   ctx.red.alloc(8);
   SNAC_CUDA(cudaMallocHost(&ctx.h_red, 8 * sizeof(double)));
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -185,10 +226,45 @@ static Field3 *field_of(Ctx &ctx, Box &b, int field, bool &ghost_alias_pp) {
   throw Error("unknown field id " + std::to_string(field));
 }
 
+// strides of the physical directions in the solver's canonical array of local box lb
+static void solver_strides(Ctx &ctx, int lb, long st[3]) {
+  const MGSolver &S = ctx.psolver;
+  const Grid3 &g = S.grid0(lb);
+  for (int sd = 0; sd < 3; ++sd) st[S.perm[sd]] = g.st(sd);
+}
+
+__global__ void permute_copy_kernel(double *dst, long d0, long d1, long d2, const double *src, long s0, long s1, long s2,
+                                    int n0, int n1, int n2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+  if (i < n0 && j < n1 && k < n2) dst[i * d0 + j * d1 + k * d2] = src[i * s0 + j * s1 + k * s2];
+}
+
 static void transfer(Ctx &ctx, int rank, int field, double *host, bool up) {
   Box &b = ctx.box_of_rank(rank);
+  const int lb = ctx.local_of_rank[rank];
+  const bool batched = ctx.prm.fft_axis > 0;
+  // spectral arrays live in the solver's canonical layout: go through a staging array
+  const bool spectral = batched && (field == SNAC_FIELD_PO || field == SNAC_FIELD_RHS_HAT);
+  Field3 *f;
   bool dummy;
-  Field3 *f = field_of(ctx, b, field, dummy);
+  if (spectral) f = &b.stage;
+  else if (field == SNAC_FIELD_RHS_HAT) f = &b.rhs;
+  else f = field_of(ctx, b, field, dummy);
+  long sst[3] = {0, 0, 0};
+  double *sp = nullptr;
+  long pint = 1 + b.g.sy + b.g.sz, sint = 0;
+  dim3 blk(32, 8, 1), grd((b.g.n[0] + 31) / 32, (b.g.n[1] + 7) / 8, b.g.n[2]);
+  if (spectral) {
+    solver_strides(ctx, lb, sst);
+    const Grid3 &sg = ctx.psolver.grid0(lb);
+    sint = 1 + sg.sy + sg.sz;
+    sp = field == SNAC_FIELD_PO ? ctx.psolver.xcur(lb) : ctx.psolver.bcur(lb);
+    if (!up) {
+      SNAC_CUDA(cudaMemsetAsync(b.stage.buf.raw, 0, b.stage.buf.elems * sizeof(double), ctx.stream));
+      permute_copy_kernel<<<grd, blk, 0, ctx.stream>>>(b.stage.p + pint, 1, b.g.sy, b.g.sz, sp + sint, sst[0], sst[1], sst[2],
+                                                       b.g.n[0], b.g.n[1], b.g.n[2]);
+    }
+  }
   cudaMemcpy3DParms prm;
   std::memset(&prm, 0, sizeof(prm));
   const size_t w = (size_t)(b.g.n[0] + 2), h = (size_t)(b.g.n[1] + 2), dpt = (size_t)(b.g.n[2] + 2);
@@ -199,6 +275,9 @@ static void transfer(Ctx &ctx, int rank, int field, double *host, bool up) {
   prm.extent = make_cudaExtent(w * sizeof(double), h, dpt);
   prm.kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
   SNAC_CUDA(cudaMemcpy3DAsync(&prm, ctx.stream));
+  if (spectral && up)
+    permute_copy_kernel<<<grd, blk, 0, ctx.stream>>>(sp + sint, sst[0], sst[1], sst[2], b.stage.p + pint, 1, b.g.sy, b.g.sz,
+                                                     b.g.n[0], b.g.n[1], b.g.n[2]);
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
@@ -226,10 +305,15 @@ static void do_boundp(Ctx &ctx, int field) {
 static void do_fft(Ctx &ctx, int dir) {
   if (ctx.prm.fft_axis == 0) throw Error("fft: the handle was created with fft_axis = 0");
   ProfScope ps(ctx, dir > 0 ? PC_FFT_FWD : PC_FFT_BWD);
-  for (auto &bp : ctx.boxes) {
-    Box &b = *bp;
-    if (dir > 0) r2r_execute(ctx, ctx.plan_p, +1, b.g, b.rhs.p, b.rhs.p, 1.0);
-    else r2r_execute(ctx, ctx.plan_p, -1, b.g, b.po.p, b.pp.p, ctx.plan_p.normfft);
+  const MGSolver &S = ctx.psolver;
+  for (int lb = 0; lb < (int)ctx.boxes.size(); ++lb) {
+    Box &b = *ctx.boxes[lb];
+    long pst[3] = {1, b.g.sy, b.g.sz}, sst[3];
+    solver_strides(ctx, lb, sst);
+    const Grid3 &sg = S.grid0(lb);
+    const long pint = 1 + b.g.sy + b.g.sz, sint = 1 + sg.sy + sg.sz;   // first interior element
+    if (dir > 0) r2r_execute(ctx, ctx.plan_p, +1, b.g.n, b.rhs.p + pint, pst, S.bcur(lb) + sint, sst, 1.0);
+    else r2r_execute(ctx, ctx.plan_p, -1, b.g.n, S.xcur(lb) + sint, sst, b.pp.p + pint, pst, ctx.plan_p.normfft);
   }
 }
 static void do_solve(Ctx &ctx) { ctx.psolver.solve(ctx); }
@@ -455,8 +539,8 @@ int snac_profile_get(snac_handle *h, int cls, double *ms, long long *launches) {
   })
 }
 const char *snac_profile_name(int cls) {
-  static const char *names[PC_COUNT] = {"rk_mom", "halo_bc", "fillps", "fft_fwd", "mg_smooth_l0", "mg_restrict_l0",
-                                        "mg_prolong_l0", "mg_coarse_levels", "fft_bwd", "correc_updt_pressure", "chkdt_chkdiv"};
+  static const char *names[PC_COUNT] = {"rk_mom", "halo_bc", "fillps", "fft_fwd", "mg_smooth_l0", "mg_down_l0",
+                                        "mg_up_l0", "mg_coarse_levels", "fft_bwd", "correc_updt_pressure", "chkdt_chkdiv"};
   return (cls >= 0 && cls < PC_COUNT) ? names[cls] : nullptr;
 }
 int snac_timer_start(snac_handle *h) { SNAC_TRY(h, SNAC_CUDA(cudaEventRecord(h->ctx.timer_ev[0], h->ctx.stream))) }

@@ -66,7 +66,7 @@ void launch_face_ops(Ctx &ctx, const DevOps<FaceOp> &ops) {
   ctx.launches++;
 }
 
-void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields) {
+void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::vector<NbTable> *nbs) {
   // `fields` holds, for each exchanged array, one entry per local box, grouped:
   // fields[f*nlocal + lb].  Ghost plane of box lb on side ib comes from the neighbour's first/last
   // interior plane (src/bound.f90:602-607).
@@ -81,7 +81,7 @@ void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields) {
         const int a = (d + 1) % 3, b = (d + 2) % 3;
         const int da = std::min(a, b), db = std::max(a, b);  // keep x (or y) fastest in the plane
         for (int ib = 0; ib < 2; ++ib) {
-          const int nbr = info.nb[d][ib];
+          const int nbr = nbs ? (*nbs)[lb].nb[d][ib] : info.nb[d][ib];
           if (nbr < 0) continue;
           const int ln = ctx.local_of_rank[nbr];
           if (ln < 0) throw Error("halo exchange with a box owned by another process is not available in this build");

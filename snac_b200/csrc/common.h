@@ -151,9 +151,13 @@ struct ExField {
 
 // Halo exchange of a group of fields (all local boxes), one direction at a time
 // (updthalo, reference src/bound.f90:587-650).
+struct NbTable {   // neighbour box ids (global, -1: none) of one local box in the array's own directions
+  int nb[3][2];
+};
 struct Exchange {
   DevOps<CopyOp> local[3];
-  void build(Ctx &ctx, const std::vector<ExField> &fields);
+  // nbs == nullptr: the boxes' physical neighbour tables
+  void build(Ctx &ctx, const std::vector<ExField> &fields, const std::vector<NbTable> *nbs = nullptr);
   void run(Ctx &ctx, int dir) const;      // one direction
   void run_all(Ctx &ctx) const {          // x, then y, then z (edges/corners propagate)
     for (int d = 0; d < 3; ++d) run(ctx, d);
@@ -202,8 +206,10 @@ void find_fft(const char bc[2], bool centered, int &kf, int &kb, double norm[2])
 void r2r_plan_init(R2RPlan &pl, int axis, int n, const char bc[2], bool centered);
 std::vector<double> r2r_eigenvalues(int n, const char bc[2], bool centered);
 // in -> out along plan.axis over the interior of a ghosted box (in == out allowed); out *= scale
-void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const Grid3 &g, const double *in, double *out,
-                 double scale);
+// in/out address the first interior element; ist/ost are the strides of the physical directions
+// x,y,z in each array (in == out with equal strides is allowed); out *= scale
+void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *in, const long ist[3],
+                 double *out, const long ost[3], double scale);
 
 // ------------------------------------------------------------------------------------------
 // multigrid (mg.cu)
@@ -233,19 +239,41 @@ struct MGLevel {
   int coarsen[3] = {0, 0, 0};      // directions coarsened going to the next level
 };
 
+// One box as seen by a linear solver.  With FFT_AXIS on, the solver works in a canonical layout:
+// direction 2 is the transform (batch) direction and directions 0,1 are the two coupled ones in
+// physical order; perm[sdir] gives the physical direction.
+struct SBox {
+  int n[3];
+  int nb[3][2];                     // neighbour box id (global) or -1
+  bool phys[3][2];                  // physical (non-periodic) boundary face
+  double sgn[3][2];                 // boundary fold sign (src/solver.f90:71-94)
+  std::vector<double> d1[3], d2[3]; // ghosted spacings: between unknowns / cell widths
+  std::vector<double> lam;          // ghosted eigenvalues/dl^2 along direction 2 (batched only)
+  double *x = nullptr, *b = nullptr; // level-0 arrays if they alias context fields (3-D solve)
+};
+
 struct MGSolver {
-  int fft_dir = -1;                // uncoupled direction (fft_axis-1) or -1
+  int fft_dir = -1;                // uncoupled direction in solver order (2 when batched) or -1
+  int perm[3] = {0, 1, 2};         // solver direction -> physical direction
+  std::vector<Field3> x0, b0;      // owned level-0 arrays (batched layout)
+  std::vector<SBox> sboxes;
   bool centered[3] = {true, true, true};
   std::vector<std::unique_ptr<MGLevel>> levels;
   std::vector<Dev1> lam;           // per local box (ghosted along the fft axis), (lambda)/dl^2
   int nq = 1;                      // number of independent planes (wavenumbers)
   DevBuf norms;                    // [2*nq]: sum r^2, sum b^2 per plane
   std::vector<double> h_norms;
+  bool plane_local = false;        // fused shared-memory path (planes not split over boxes)
+  int first_smem_level = 0;        // first level handled by the one-CTA-per-plane kernel
+  std::vector<Field3> x1;          // second x buffer of the tiled levels [level*nbox + box]
   int last_iters = 0;
   double last_relres = 0.0;
   double alpha = 0.0;              // extra diagonal shift (IMPDIFF: alphai)
-  void setup(Ctx &ctx, const bool centered_[3]);
+  void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched);
   void solve(Ctx &ctx);
+  const Grid3 &grid0(int lb) const { return levels[0]->boxes[lb].g; }
+  double *xcur(int lb) const { return levels[0]->boxes[lb].xp; }
+  double *bcur(int lb) const { return levels[0]->boxes[lb].bp; }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -258,6 +286,7 @@ struct Box {
   Dev1 dc[3], df[3], rdc[3], rdf[3];
   Field3 u[2], v[2], w[2];  // double-buffered velocity (rk_mom writes the other parity)
   Field3 p, pp, rhs, po;
+  Field3 stage;             // staging array for transfers of spectral fields (batched solves)
   Field3 du, dv, dw;        // d?dtrko
   Field3 s[SNAC_MAX_SCAL], ds[SNAC_MAX_SCAL];
   // Poisson RHS: weights (cell width, or 1 along the transform axis), 1/width along the transform
@@ -271,7 +300,7 @@ struct Box {
 
 // per-kernel-class device timing (enabled by snac_profile_enable; serialises the stream)
 enum ProfClass : int {
-  PC_RK_MOM = 0, PC_HALO_BC, PC_FILLPS, PC_FFT_FWD, PC_MG_SMOOTH0, PC_MG_RESTRICT0, PC_MG_PROLONG0, PC_MG_COARSE,
+  PC_RK_MOM = 0, PC_HALO_BC, PC_FILLPS, PC_FFT_FWD, PC_MG_SMOOTH0, PC_MG_DOWN0, PC_MG_UP0, PC_MG_COARSE,
   PC_FFT_BWD, PC_CORREC, PC_CHK, PC_COUNT
 };
 

@@ -148,45 +148,38 @@ void r2r_plan_init(R2RPlan &pl, int axis, int n, const char bc[2], bool centered
 // device
 // ------------------------------------------------------------------------------------------
 struct R2RArgs {
-  const double *in;
-  double *out;
-  long sy, sz;       // strides of the ghosted box
+  const double *in;  // first interior element of the input array
+  double *out;       // first interior element of the output array
+  long ist[3], ost[3];  // strides of the physical directions x,y,z in the input / output arrays
   int n[3];
   int axis;
   int nt;            // transform length
   int tp;            // pencils per tile
+  int pd, od;        // direction along which a tile gathers pencils; the remaining direction
   int kind;
+  int in_lane_t, out_lane_t;  // consecutive lanes walk along the transform axis (it has stride 1)
   double scale;
   const double *tab; // twiddles (fast) or dense matrix (generic)
 };
 
-// pencil p of tile `tile` -> offset of its first interior element; returns false if out of range
-__device__ inline bool pencil_base(const R2RArgs &a, int tile, int p, long &base) {
-  if (a.axis == 0) {
-    const long q = (long)tile * a.tp + p;
-    if (q >= (long)a.n[1] * a.n[2]) return false;
-    const int j = (int)(q % a.n[1]), k = (int)(q / a.n[1]);
-    base = 1 + (j + 1) * a.sy + (k + 1) * a.sz;
-    return true;
-  }
-  const int ntx = (a.n[0] + a.tp - 1) / a.tp;
-  const int tx = tile % ntx, o = tile / ntx;
-  const int i = tx * a.tp + p;
-  if (i >= a.n[0]) return false;
-  if (a.axis == 1) base = (1 + i) + a.sy + (o + 1) * a.sz;
-  else base = (1 + i) + (o + 1) * a.sy + a.sz;
+// pencil p of tile `tile` -> offsets of its first element in the two arrays; false if out of range
+__device__ inline bool pencil_base(const R2RArgs &a, int tile, int p, long &ib, long &ob) {
+  const int ntp = (a.n[a.pd] + a.tp - 1) / a.tp;
+  const int tpi = tile % ntp, o = tile / ntp;
+  const int ip = tpi * a.tp + p;
+  if (ip >= a.n[a.pd]) return false;
+  ib = ip * a.ist[a.pd] + o * a.ist[a.od];
+  ob = ip * a.ost[a.pd] + o * a.ost[a.od];
   return true;
 }
 
-__device__ inline long axis_stride(const R2RArgs &a) { return a.axis == 0 ? 1 : (a.axis == 1 ? a.sy : a.sz); }
-
 // iterate work items (p, t) with the lane-fastest index chosen for coalescing
-#define FOR_ITEMS(NT_, ...)                                                              \
+#define FOR_ITEMS(LANE_T_, NT_, ...)                                                     \
   {                                                                                      \
     const int tot_ = (NT_) * tp;                                                         \
     for (int it_ = threadIdx.x; it_ < tot_; it_ += blockDim.x) {                         \
       int p, t;                                                                          \
-      if (a.axis == 0) { t = it_ % (NT_); p = it_ / (NT_); } else { p = it_ % tp; t = it_ / tp; } \
+      if (LANE_T_) { t = it_ % (NT_); p = it_ / (NT_); } else { p = it_ % tp; t = it_ / tp; } \
       __VA_ARGS__                                                                        \
     }                                                                                    \
   }
@@ -194,16 +187,16 @@ __device__ inline long axis_stride(const R2RArgs &a) { return a.axis == 0 ? 1 : 
 __global__ void __launch_bounds__(256) r2r_dense_kernel(const R2RArgs a) {
   extern __shared__ double T[];
   const int tp = a.tp, tpp = a.tp + 1, nt = a.nt;
-  const long sa = axis_stride(a);
+  const long isa = a.ist[a.axis], osa = a.ost[a.axis];
   const int nfull = a.n[a.axis];
-  FOR_ITEMS(nfull, {
-    long base;
-    if (pencil_base(a, blockIdx.x, p, base)) T[t * tpp + p] = a.in[base + t * sa];
+  FOR_ITEMS(a.in_lane_t, nfull, {
+    long ib, ob;
+    if (pencil_base(a, blockIdx.x, p, ib, ob)) T[t * tpp + p] = a.in[ib + t * isa];
   })
   __syncthreads();
-  FOR_ITEMS(nfull, {
-    long base;
-    if (pencil_base(a, blockIdx.x, p, base)) {
+  FOR_ITEMS(a.out_lane_t, nfull, {
+    long ib, ob;
+    if (pencil_base(a, blockIdx.x, p, ib, ob)) {
       double acc;
       if (t < nt) {
         acc = 0.0;
@@ -212,7 +205,7 @@ __global__ void __launch_bounds__(256) r2r_dense_kernel(const R2RArgs a) {
       } else {
         acc = T[t * tpp + p];  // entries beyond the transform length (staggered, q = 1) pass through
       }
-      a.out[base + t * sa] = acc * a.scale;
+      a.out[ob + t * osa] = acc * a.scale;
     }
   })
 }
@@ -228,7 +221,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
   extern __shared__ double T[];
   const int tp = a.tp, tpp = a.tp + 1, n = a.nt, m = n >> 1;
   const int bits = 31 - __clz(m);
-  const long sa = axis_stride(a);
+  const long isa = a.ist[a.axis], osa = a.ost[a.axis];
   const double *tw = a.tab;                 // e^{-2 pi i q/m}, q < m/2
   const double *wn = a.tab + 2 * (m / 2);   // e^{-2 pi i k/n}, k <= m/2
   const double *wd = wn + 2 * (m / 2 + 1);  // e^{-i pi k/(2n)}, k <= m
@@ -238,10 +231,10 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
 
   if (FWD) {
     // 1. load (with the even/odd permutation of the DCT-II algorithm and the (-1)^j of DST-II)
-    FOR_ITEMS(n, {
-      long base;
-      if (pencil_base(a, blockIdx.x, p, base)) {
-        double v = a.in[base + t * sa];
+    FOR_ITEMS(a.in_lane_t, n, {
+      long ib, ob;
+      if (pencil_base(a, blockIdx.x, p, ib, ob)) {
+        double v = a.in[ib + t * isa];
         int slot = t;
         if (makhoul) {
           if (sine && (t & 1)) v = -v;
@@ -270,10 +263,10 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
       __syncthreads();
     }
     // 3. untangle + post-twiddle, written straight to global memory
-    FOR_ITEMS(nk, {
-      long base;
+    FOR_ITEMS(a.out_lane_t, nk, {
+      long ib, ob;
       const int k = t;
-      if (pencil_base(a, blockIdx.x, p, base)) {
+      if (pencil_base(a, blockIdx.x, p, ib, ob)) {
         const int bk = brev(k, bits), bmk = brev((m - k) & (m - 1), bits);
         const C2 zk{T[(2 * bk) * tpp + p], T[(2 * bk + 1) * tpp + p]};
         const C2 zm{T[(2 * bmk) * tpp + p], T[(2 * bmk + 1) * tpp + p]};
@@ -283,52 +276,52 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
         const C2 wo = cmul(w, o);
         const C2 xk{e.x + wo.x, e.y + wo.y};        // X[k]
         const C2 xmk{e.x - wo.x, -(e.y - wo.y)};    // X[m-k]
-        const int ka = (k == 0) ? 0 : k, kb = m - k; // the two output wavenumbers (k=0: 0 and m)
-        double *out = a.out + base;
+        const int ka = k, kb = m - k;               // the two output wavenumbers (k=0: 0 and m)
+        double *out = a.out + ob;
         const double sc = a.scale;
         if (!makhoul) {
-          out[ka * sa] = sc * xk.x;
-          if (k > 0) out[(n - ka) * sa] = sc * xk.y;
-          out[kb * sa] = sc * xmk.x;
-          if (k > 0 && kb < m) out[(n - kb) * sa] = sc * xmk.y;
+          out[ka * osa] = sc * xk.x;
+          if (k > 0) out[(n - ka) * osa] = sc * xk.y;
+          out[kb * osa] = sc * xmk.x;
+          if (k > 0 && kb < m) out[(n - kb) * osa] = sc * xmk.y;
         } else {
           // X_c[k] = 2 Re(e^{-i pi k/2n} V[k]), X_c[n-k] = -2 Im(e^{-i pi k/2n} V[k])
           {
             const double c = __ldg(wd + 2 * ka), s_ = -__ldg(wd + 2 * ka + 1);
             const double v0 = 2.0 * (c * xk.x + s_ * xk.y), v1 = 2.0 * (s_ * xk.x - c * xk.y);
             const int o0 = sine ? (n - 1 - ka) : ka;
-            out[o0 * sa] = sc * v0;
-            if (ka > 0) { const int o1 = sine ? (ka - 1) : (n - ka); out[o1 * sa] = sc * v1; }
+            out[o0 * osa] = sc * v0;
+            if (ka > 0) { const int o1 = sine ? (ka - 1) : (n - ka); out[o1 * osa] = sc * v1; }
           }
           {
             const double c = __ldg(wd + 2 * kb), s_ = -__ldg(wd + 2 * kb + 1);
             const double v0 = 2.0 * (c * xmk.x + s_ * xmk.y), v1 = 2.0 * (s_ * xmk.x - c * xmk.y);
             const int o0 = sine ? (n - 1 - kb) : kb;
-            out[o0 * sa] = sc * v0;
-            if (kb < m) { const int o1 = sine ? (kb - 1) : (n - kb); out[o1 * sa] = sc * v1; }
+            out[o0 * osa] = sc * v0;
+            if (kb < m) { const int o1 = sine ? (kb - 1) : (n - kb); out[o1 * osa] = sc * v1; }
           }
         }
       }
     })
   } else {
     // 1. global load + pre-twiddle + inverse untangle into bit-reversed slots
-    FOR_ITEMS(nk, {
-      long base;
+    FOR_ITEMS(a.in_lane_t, nk, {
+      long ib, ob;
       const int k = t;
-      if (pencil_base(a, blockIdx.x, p, base)) {
-        const double *in = a.in + base;
+      if (pencil_base(a, blockIdx.x, p, ib, ob)) {
+        const double *in = a.in + ib;
         const int kb = m - k;
         C2 xk, xm;  // X[k], X[m-k]
         if (!makhoul) {
-          xk.x = in[k * sa];  xk.y = (k > 0) ? in[(n - k) * sa] : 0.0;
-          xm.x = in[kb * sa]; xm.y = (kb < m) ? in[(n - kb) * sa] : 0.0;
+          xk.x = in[k * isa];  xk.y = (k > 0) ? in[(n - k) * isa] : 0.0;
+          xm.x = in[kb * isa]; xm.y = (kb < m) ? in[(n - kb) * isa] : 0.0;
         } else {
           auto getx = [&](int kk) -> C2 {
             const double c = __ldg(wd + 2 * kk), s_ = -__ldg(wd + 2 * kk + 1);
             const int i0 = sine ? (n - 1 - kk) : kk;
-            const double a0 = in[i0 * sa];
+            const double a0 = in[i0 * isa];
             double a1 = 0.0;
-            if (kk > 0) { const int i1 = sine ? (kk - 1) : (n - kk); a1 = in[i1 * sa]; }
+            if (kk > 0) { const int i1 = sine ? (kk - 1) : (n - kk); a1 = in[i1 * isa]; }
             return C2{c * a0 + s_ * a1, s_ * a0 - c * a1};
           };
           xk = getx(k);
@@ -368,43 +361,39 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
       __syncthreads();
     }
     // 3. store (inverse of the forward load mapping)
-    FOR_ITEMS(n, {
-      long base;
-      if (pencil_base(a, blockIdx.x, p, base)) {
+    FOR_ITEMS(a.out_lane_t, n, {
+      long ib, ob;
+      if (pencil_base(a, blockIdx.x, p, ib, ob)) {
         int slot = t;
         if (makhoul) slot = (t & 1) ? (n - 1 - (t >> 1)) : (t >> 1);
         double v = T[slot * tpp + p] * a.scale;
         if (makhoul && sine && (t & 1)) v = -v;
-        a.out[base + t * sa] = v;
+        a.out[ob + t * osa] = v;
       }
     })
   }
 }
 
-void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const Grid3 &g, const double *in, double *out,
-                 double scale) {
+void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *in, const long ist[3],
+                 double *out, const long ost[3], double scale) {
   R2RArgs a;
   a.in = in; a.out = out;
-  a.sy = g.sy; a.sz = g.sz;
-  for (int d = 0; d < 3; ++d) a.n[d] = g.n[d];
+  for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = ist[d]; a.ost[d] = ost[d]; }
   a.axis = pl.axis;
   a.nt = pl.nt;
   a.kind = dir > 0 ? pl.kind_fwd : pl.kind_bwd;
   a.scale = scale;
-  const int n = g.n[pl.axis];
+  const int n = n3[pl.axis];
   if (n != pl.n) throw Error("r2r_execute: box size differs from the planned transform length");
+  a.pd = pl.axis == 0 ? 1 : 0;
+  a.od = 3 - pl.axis - a.pd;
+  a.in_lane_t = (ist[pl.axis] == 1);
+  a.out_lane_t = (ost[pl.axis] == 1);
   int tp = 16;
   while (tp > 1 && (size_t)n * (tp + 1) * sizeof(double) > 200 * 1024) tp >>= 1;
-  if (pl.axis == 0) {
-    const long np = (long)g.n[1] * g.n[2];
-    while (tp > 1 && np < tp) tp >>= 1;
-  } else {
-    while (tp > 1 && g.n[0] < tp) tp >>= 1;
-  }
+  while (tp > 1 && n3[a.pd] < tp) tp >>= 1;
   a.tp = tp;
-  long ntiles;
-  if (pl.axis == 0) ntiles = ((long)g.n[1] * g.n[2] + tp - 1) / tp;
-  else ntiles = (long)((g.n[0] + tp - 1) / tp) * (pl.axis == 1 ? g.n[2] : g.n[1]);
+  const long ntiles = (long)((n3[a.pd] + tp - 1) / tp) * n3[a.od];
   const size_t smem = (size_t)n * (tp + 1) * sizeof(double);
   if (pl.fast) {
     a.tab = pl.twiddle.p();

@@ -23,7 +23,8 @@
 // re-discretised coarse operators (coarse cell width = sum of its two children), residual
 // summation for restriction and piecewise-constant prolongation.  Directions are coarsened only
 // while their mesh width is within a factor 1.5 of the finest one (semi-coarsening for anisotropic
-// grids), and only while every box keeps an even size.
+// grids).  A box of odd size keeps its last cell unpaired, so coarsening continues down to one
+// cell per box and direction.
 #include <algorithm>
 #include <cmath>
 
@@ -80,9 +81,10 @@ __global__ void __launch_bounds__(256) mg_restrict_kernel(const MGKernelBox F, d
   const bool active = (I <= cn0 && J <= cn1 && K <= cn2);
   double rsum = 0.0, r2 = 0.0, b2 = 0.0;
   if (active) {
-    const int i0 = c0 ? 2 * I - 1 : I, i1 = c0 ? 2 * I : I;
-    const int j0 = c1 ? 2 * J - 1 : J, j1 = c1 ? 2 * J : J;
-    const int k0 = c2 ? 2 * K - 1 : K, k1 = c2 ? 2 * K : K;
+    // children of a coarse cell: the pair (2I-1, 2I); an odd fine size leaves the last one single
+    const int i0 = c0 ? 2 * I - 1 : I, i1 = c0 ? min(2 * I, F.n[0]) : I;
+    const int j0 = c1 ? 2 * J - 1 : J, j1 = c1 ? min(2 * J, F.n[1]) : J;
+    const int k0 = c2 ? 2 * K - 1 : K, k1 = c2 ? min(2 * K, F.n[2]) : K;
     for (int k = k0; k <= k1; ++k)
       for (int j = j0; j <= j1; ++j)
         for (int i = i0; i <= i1; ++i) {
@@ -152,10 +154,333 @@ __global__ void mg_fill_along_kernel(double *x, long sy, long sz, int n0, int n1
 }
 
 // ------------------------------------------------------------------------------------------
+// plane-local fast path (batched 2-D problems whose planes are not split over boxes)
+//
+// Canonical layout: directions 0,1 are the coupled ones (0 fastest), direction 2 is the batch
+// (wavenumber).  A V(1,1) cycle touches each fine level with two fused kernels,
+//   down: red sweep + black sweep + residual + restriction      (read x, b; write x', coarse b)
+//   up  : correction from the coarse level + black sweep + red sweep   (read x', b, coarse x; write x)
+// working on shared-memory tiles with a halo wide enough to recompute the neighbours' updates
+// (3 cells down, 2 cells up); x is ping-ponged between two buffers so that tiles never read what
+// another tile has already overwritten.  All levels whose plane fits in shared memory are done by
+// one kernel (one CTA per wavenumber) that runs the rest of the V-cycle without leaving the SM.
+// ------------------------------------------------------------------------------------------
+struct PLevel {
+  int n1, n2;
+  long sy, sz;        // row / plane strides of this level's global arrays
+  const double *am1, *ap1, *ad1, *w1, *am2, *ap2, *ad2, *w2;  // ghosted, index 1..n
+  int c1, c2;         // coarsening towards the next level
+  int per1, per2;     // periodic wrap onto the box itself
+};
+
+constexpr int PT_X = 64, PT_Y = 32;     // tile interior
+constexpr int PH_D = 3, PH_U = 2;       // halo of the down / up kernels
+
+__device__ inline int wrap1(int g, int n) {  // 1-based periodic wrap, valid for -n < g <= 2n
+  return g < 1 ? g + n : (g > n ? g - n : g);
+}
+
+// loads the tile of x (and b) and the 1-D coefficients; cells outside a non-periodic domain get
+// zero values and zero coefficients (they are never updated)
+template <int H>
+__device__ inline void ptile_load(const PLevel &L, const double *x, const double *b, long qoff, int i0, int j0,
+                                  double *sx, double *sb, double *c1, double *c2) {
+  constexpr int W = PT_X + 2 * H, Ht = PT_Y + 2 * H;
+  for (int t = threadIdx.x; t < W; t += blockDim.x) {
+    const int gu = i0 + t - H;
+    const bool ok = L.per1 || (gu >= 1 && gu <= L.n1);
+    const int gi = L.per1 ? wrap1(gu, L.n1) : gu;
+    c1[t] = ok ? __ldg(L.am1 + gi) : 0.0; c1[W + t] = ok ? __ldg(L.ap1 + gi) : 0.0;
+    c1[2 * W + t] = ok ? __ldg(L.ad1 + gi) : 0.0; c1[3 * W + t] = ok ? __ldg(L.w1 + gi) : 0.0;
+  }
+  for (int t = threadIdx.x; t < Ht; t += blockDim.x) {
+    const int gv = j0 + t - H;
+    const bool ok = L.per2 || (gv >= 1 && gv <= L.n2);
+    const int gj = L.per2 ? wrap1(gv, L.n2) : gv;
+    c2[t] = ok ? __ldg(L.am2 + gj) : 0.0; c2[Ht + t] = ok ? __ldg(L.ap2 + gj) : 0.0;
+    c2[2 * Ht + t] = ok ? __ldg(L.ad2 + gj) : 0.0; c2[3 * Ht + t] = ok ? __ldg(L.w2 + gj) : 0.0;
+  }
+  for (int t = threadIdx.x; t < W * Ht; t += blockDim.x) {
+    const int ti = t % W, tj = t / W;
+    const int gu = i0 + ti - H, gv = j0 + tj - H;
+    const bool ok = (L.per1 || (gu >= 1 && gu <= L.n1)) && (L.per2 || (gv >= 1 && gv <= L.n2));
+    double vx = 0.0, vb = 0.0;
+    if (ok) {
+      const int gi = L.per1 ? wrap1(gu, L.n1) : gu, gj = L.per2 ? wrap1(gv, L.n2) : gv;
+      const long o = qoff + gi + L.sy * gj;
+      vx = x ? x[o] : 0.0;
+      vb = b[o];
+    }
+    sx[t] = vx;
+    sb[t] = vb;
+  }
+}
+
+// one colour of a Gauss-Seidel sweep on the tile cells whose ring index is >= ring
+template <int H>
+__device__ inline void ptile_sweep(const PLevel &L, int i0, int j0, int color, int ring, double *sx, const double *sb,
+                                   const double *c1, const double *c2, double lam) {
+  constexpr int W = PT_X + 2 * H, Ht = PT_Y + 2 * H;
+  const int wi = W - 2 * ring, hj = Ht - 2 * ring;
+  const int half = wi / 2;  // W is even
+  for (int t = threadIdx.x; t < half * hj; t += blockDim.x) {
+    const int tj = ring + t / half;
+    const int gv = j0 + tj - H;
+    // first cell of this colour in the row: parity of (gu + gv) with gu = i0 + ti - H
+    int ti = ring + 2 * (t % half);
+    if (((i0 + ti - H + gv) & 1) != color) ti += 1;
+    const int gu = i0 + ti - H;
+    if (!((L.per1 || (gu >= 1 && gu <= L.n1)) && (L.per2 || (gv >= 1 && gv <= L.n2)))) continue;
+    const double w1 = c1[3 * W + ti], w2 = c2[3 * Ht + tj];
+    const double diag = w2 * c1[2 * W + ti] + w1 * c2[2 * Ht + tj] + lam * w1 * w2;
+    if (diag == 0.0) continue;
+    const int c = ti + W * tj;
+    const double off = w2 * (c1[ti] * sx[c - 1] + c1[W + ti] * sx[c + 1]) + w1 * (c2[tj] * sx[c - W] + c2[Ht + tj] * sx[c + W]);
+    sx[c] = (sb[c] - off) / diag;
+  }
+}
+
+__global__ void __launch_bounds__(256) mg_plane_down_kernel(const PLevel L, const double *xin, double *xout, const double *b,
+                                                            double *cb, long csy, long csz, const double *lamq, double alpha,
+                                                            double *norms, int nq, int want_b) {
+  constexpr int H = PH_D, W = PT_X + 2 * H, Ht = PT_Y + 2 * H;
+  __shared__ double sx[W * Ht], sb[W * Ht], c1[4 * W], c2[4 * Ht];
+  const int q = blockIdx.z;
+  const int i0 = 1 + blockIdx.x * PT_X, j0 = 1 + blockIdx.y * PT_Y;
+  const long qoff = (long)(q + 1) * L.sz;
+  const double lam = alpha + __ldg(lamq + q + 1);
+  ptile_load<H>(L, xin, b, qoff, i0, j0, sx, sb, c1, c2);
+  __syncthreads();
+  ptile_sweep<H>(L, i0, j0, 0, 1, sx, sb, c1, c2, lam);
+  __syncthreads();
+  ptile_sweep<H>(L, i0, j0, 1, 2, sx, sb, c1, c2, lam);
+  __syncthreads();
+  // residual on the interior (into sb), new x to global
+  double r2 = 0.0, b2 = 0.0;
+  for (int t = threadIdx.x; t < PT_X * PT_Y; t += blockDim.x) {
+    const int ti = H + t % PT_X, tj = H + t / PT_X;
+    const int gu = i0 + ti - H, gv = j0 + tj - H;
+    const int c = ti + W * tj;
+    double r = 0.0;
+    if (gu <= L.n1 && gv <= L.n2) {
+      const double w1 = c1[3 * W + ti], w2 = c2[3 * Ht + tj];
+      const double diag = w2 * c1[2 * W + ti] + w1 * c2[2 * Ht + tj] + lam * w1 * w2;
+      const double off = w2 * (c1[ti] * sx[c - 1] + c1[W + ti] * sx[c + 1]) + w1 * (c2[tj] * sx[c - W] + c2[Ht + tj] * sx[c + W]);
+      const double bb = sb[c];
+      r = bb - (diag * sx[c] + off);
+      r2 += r * r;
+      b2 += bb * bb;
+      xout[qoff + gu + L.sy * gv] = sx[c];
+    }
+    sb[c] = r;   // each cell is read and written by the same thread only
+  }
+  __syncthreads();
+  // restriction: sum of the children's residuals
+  if (cb) {
+    const int cw = L.c1 ? PT_X / 2 : PT_X, ch = L.c2 ? PT_Y / 2 : PT_Y;
+    const int cn1 = L.c1 ? (L.n1 + 1) / 2 : L.n1, cn2 = L.c2 ? (L.n2 + 1) / 2 : L.n2;
+    const int I0 = L.c1 ? (i0 + 1) / 2 : i0, J0 = L.c2 ? (j0 + 1) / 2 : j0;
+    for (int t = threadIdx.x; t < cw * ch; t += blockDim.x) {
+      const int ci = t % cw, cj = t / cw;
+      const int I = I0 + ci, J = J0 + cj;
+      if (I > cn1 || J > cn2) continue;
+      const int ti0 = H + (L.c1 ? 2 * ci : ci), tj0 = H + (L.c2 ? 2 * cj : cj);
+      double s = 0.0;
+      for (int dj = 0; dj <= L.c2; ++dj)
+        for (int di = 0; di <= L.c1; ++di) s += sb[(ti0 + di) + W * (tj0 + dj)];  // cells past the domain hold r = 0
+      cb[(long)(q + 1) * csz + I + csy * J] = s;
+    }
+  }
+  if (norms) {
+    for (int o = 16; o > 0; o >>= 1) {
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    }
+    __shared__ double red[2][8];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = r2; red[1][threadIdx.x >> 5] = b2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { r2 += red[0][w]; b2 += red[1][w]; }
+      atomicAdd(norms + q, r2);
+      if (want_b) atomicAdd(norms + nq + q, b2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) mg_plane_up_kernel(const PLevel L, const double *xin, double *xout, const double *b,
+                                                          const double *cx, long csy, long csz, const double *lamq,
+                                                          double alpha) {
+  constexpr int H = PH_U, W = PT_X + 2 * H, Ht = PT_Y + 2 * H;
+  __shared__ double sx[W * Ht], sb[W * Ht], c1[4 * W], c2[4 * Ht];
+  const int q = blockIdx.z;
+  const int i0 = 1 + blockIdx.x * PT_X, j0 = 1 + blockIdx.y * PT_Y;
+  const long qoff = (long)(q + 1) * L.sz;
+  const double lam = alpha + __ldg(lamq + q + 1);
+  ptile_load<H>(L, xin, b, qoff, i0, j0, sx, sb, c1, c2);
+  // coarse-grid correction (piecewise constant prolongation)
+  for (int t = threadIdx.x; t < W * Ht; t += blockDim.x) {
+    const int ti = t % W, tj = t / W;
+    const int gu = i0 + ti - H, gv = j0 + tj - H;
+    if (!((L.per1 || (gu >= 1 && gu <= L.n1)) && (L.per2 || (gv >= 1 && gv <= L.n2)))) continue;
+    const int gi = L.per1 ? wrap1(gu, L.n1) : gu, gj = L.per2 ? wrap1(gv, L.n2) : gv;
+    const int I = L.c1 ? (gi + 1) >> 1 : gi, J = L.c2 ? (gj + 1) >> 1 : gj;
+    sx[t] += __ldg(cx + (long)(q + 1) * csz + I + csy * J);   // same thread loaded sx[t]
+  }
+  __syncthreads();
+  ptile_sweep<H>(L, i0, j0, 1, 1, sx, sb, c1, c2, lam);
+  __syncthreads();
+  ptile_sweep<H>(L, i0, j0, 0, 2, sx, sb, c1, c2, lam);
+  __syncthreads();
+  for (int t = threadIdx.x; t < PT_X * PT_Y; t += blockDim.x) {
+    const int ti = H + t % PT_X, tj = H + t / PT_X;
+    const int gu = i0 + ti - H, gv = j0 + tj - H;
+    if (gu <= L.n1 && gv <= L.n2) xout[qoff + gu + L.sy * gv] = sx[ti + W * tj];
+  }
+}
+
+// ---- whole coarse part of the V-cycle in shared memory: one CTA per wavenumber ----------------
+constexpr int PMAXLEV = 16;
+struct PCoarseArgs {
+  PLevel lev[PMAXLEV];
+  int nlev;
+  const double *b;       // right-hand side of the top level
+  const double *xin;     // initial iterate of the top level, or nullptr (zero)
+  double *xout;          // result on the top level
+  const double *lamq;
+  double alpha;
+  double *norms;         // only when the top level is level 0
+  int nq, want_b;
+  int npre, npost, nbot;
+};
+
+__device__ inline void pc_sweep(const PLevel &L, double *x, const double *b, int color, double lam) {
+  const int n1 = L.n1, n2 = L.n2;
+  for (int t = threadIdx.x; t < n1 * n2; t += blockDim.x) {
+    const int i = t % n1 + 1, j = t / n1 + 1;
+    if (((i + j) & 1) != color) continue;
+    const double w1 = __ldg(L.w1 + i), w2 = __ldg(L.w2 + j);
+    const double diag = w2 * __ldg(L.ad1 + i) + w1 * __ldg(L.ad2 + j) + lam * w1 * w2;
+    if (diag == 0.0) continue;
+    const int im = i > 1 ? i - 1 : (L.per1 ? n1 : 1), ip = i < n1 ? i + 1 : (L.per1 ? 1 : n1);
+    const int jm = j > 1 ? j - 1 : (L.per2 ? n2 : 1), jp = j < n2 ? j + 1 : (L.per2 ? 1 : n2);
+    const double off = w2 * (__ldg(L.am1 + i) * x[(im - 1) + n1 * (j - 1)] + __ldg(L.ap1 + i) * x[(ip - 1) + n1 * (j - 1)]) +
+                       w1 * (__ldg(L.am2 + j) * x[(i - 1) + n1 * (jm - 1)] + __ldg(L.ap2 + j) * x[(i - 1) + n1 * (jp - 1)]);
+    x[t] = (b[t] - off) / diag;
+  }
+  __syncthreads();
+}
+
+__device__ inline double pc_resid(const PLevel &L, const double *x, const double *b, int i, int j, double lam) {
+  const int n1 = L.n1, n2 = L.n2;
+  const double w1 = __ldg(L.w1 + i), w2 = __ldg(L.w2 + j);
+  const double diag = w2 * __ldg(L.ad1 + i) + w1 * __ldg(L.ad2 + j) + lam * w1 * w2;
+  const int im = i > 1 ? i - 1 : (L.per1 ? n1 : 1), ip = i < n1 ? i + 1 : (L.per1 ? 1 : n1);
+  const int jm = j > 1 ? j - 1 : (L.per2 ? n2 : 1), jp = j < n2 ? j + 1 : (L.per2 ? 1 : n2);
+  const double off = w2 * (__ldg(L.am1 + i) * x[(im - 1) + n1 * (j - 1)] + __ldg(L.ap1 + i) * x[(ip - 1) + n1 * (j - 1)]) +
+                     w1 * (__ldg(L.am2 + j) * x[(i - 1) + n1 * (jm - 1)] + __ldg(L.ap2 + j) * x[(i - 1) + n1 * (jp - 1)]);
+  return b[(i - 1) + n1 * (j - 1)] - (diag * x[(i - 1) + n1 * (j - 1)] + off);
+}
+
+__global__ void __launch_bounds__(256) mg_plane_coarse_kernel(const PCoarseArgs a) {
+  extern __shared__ double sm[];
+  const int q = blockIdx.x;
+  const double lam = a.alpha + __ldg(a.lamq + q + 1);
+  // shared-memory layout: x_l, b_l for every level
+  double *xs[PMAXLEV], *bs[PMAXLEV];
+  {
+    double *p = sm;
+    for (int l = 0; l < a.nlev; ++l) {
+      const int sz = a.lev[l].n1 * a.lev[l].n2;
+      xs[l] = p; p += sz;
+      bs[l] = p; p += sz;
+    }
+  }
+  {
+    const PLevel &T = a.lev[0];
+    const long qoff = (long)(q + 1) * T.sz;
+    for (int t = threadIdx.x; t < T.n1 * T.n2; t += blockDim.x) {
+      const long o = qoff + (t % T.n1 + 1) + T.sy * (t / T.n1 + 1);
+      bs[0][t] = a.b[o];
+      xs[0][t] = a.xin ? a.xin[o] : 0.0;
+    }
+    __syncthreads();
+  }
+  double r2 = 0.0, b2 = 0.0;
+  for (int l = 0; l < a.nlev - 1; ++l) {
+    const PLevel &F = a.lev[l];
+    for (int s = 0; s < a.npre; ++s) { pc_sweep(F, xs[l], bs[l], 0, lam); pc_sweep(F, xs[l], bs[l], 1, lam); }
+    const PLevel &C = a.lev[l + 1];
+    for (int t = threadIdx.x; t < C.n1 * C.n2; t += blockDim.x) {
+      const int I = t % C.n1 + 1, J = t / C.n1 + 1;
+      const int i0 = F.c1 ? 2 * I - 1 : I, i1 = F.c1 ? min(2 * I, F.n1) : I;
+      const int j0 = F.c2 ? 2 * J - 1 : J, j1 = F.c2 ? min(2 * J, F.n2) : J;
+      double s = 0.0;
+      for (int j = j0; j <= j1; ++j)
+        for (int i = i0; i <= i1; ++i) {
+          const double r = pc_resid(F, xs[l], bs[l], i, j, lam);
+          s += r;
+          if (l == 0 && a.norms) {
+            r2 += r * r;
+            const double bb = bs[0][(i - 1) + F.n1 * (j - 1)];
+            b2 += bb * bb;
+          }
+        }
+      bs[l + 1][t] = s;
+      xs[l + 1][t] = 0.0;
+    }
+    __syncthreads();
+  }
+  {
+    const int l = a.nlev - 1;
+    const PLevel &B = a.lev[l];
+    const int ns = (a.nlev == 1) ? a.nbot : a.nbot;
+    for (int s = 0; s < ns; ++s) { pc_sweep(B, xs[l], bs[l], 0, lam); pc_sweep(B, xs[l], bs[l], 1, lam); }
+    if (a.nlev == 1 && a.norms) {
+      for (int t = threadIdx.x; t < B.n1 * B.n2; t += blockDim.x) {
+        const double r = pc_resid(B, xs[l], bs[l], t % B.n1 + 1, t / B.n1 + 1, lam);
+        r2 += r * r;
+        b2 += bs[l][t] * bs[l][t];
+      }
+    }
+  }
+  for (int l = a.nlev - 2; l >= 0; --l) {
+    const PLevel &F = a.lev[l];
+    const PLevel &C = a.lev[l + 1];
+    for (int t = threadIdx.x; t < F.n1 * F.n2; t += blockDim.x) {
+      const int i = t % F.n1 + 1, j = t / F.n1 + 1;
+      const int I = F.c1 ? (i + 1) >> 1 : i, J = F.c2 ? (j + 1) >> 1 : j;
+      xs[l][t] += xs[l + 1][(I - 1) + C.n1 * (J - 1)];
+    }
+    __syncthreads();
+    for (int s = 0; s < a.npost; ++s) { pc_sweep(F, xs[l], bs[l], 1, lam); pc_sweep(F, xs[l], bs[l], 0, lam); }
+  }
+  {
+    const PLevel &T = a.lev[0];
+    const long qoff = (long)(q + 1) * T.sz;
+    for (int t = threadIdx.x; t < T.n1 * T.n2; t += blockDim.x)
+      a.xout[qoff + (t % T.n1 + 1) + T.sy * (t / T.n1 + 1)] = xs[0][t];
+  }
+  if (a.norms) {
+    for (int o = 16; o > 0; o >>= 1) {
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    }
+    __shared__ double red[2][8];
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = r2; red[1][threadIdx.x >> 5] = b2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { r2 += red[0][w]; b2 += red[1][w]; }
+      atomicAdd(a.norms + q, r2);
+      if (a.want_b) atomicAdd(a.norms + a.nq + q, b2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
 static dim3 mg_block(const Grid3 &g, int fft_dir) {
-  // threads of a block must share the plane index along y or z when that is the batch direction
+  // threads of a block must share the plane index along z when that is the batch direction
   dim3 b;
   if (g.n[0] <= 8) b = dim3(8, 8, 4);
   else if (g.n[0] <= 32) b = dim3(32, 8, 1);
@@ -202,71 +527,53 @@ static void build_dir(MGLevelBox &L, int d, bool coupled, const std::vector<doub
   L.am[d].upload(am); L.ap[d].upload(ap); L.ad[d].upload(ad); L.w[d].upload(w);
 }
 
-void MGSolver::setup(Ctx &ctx, const bool centered_[3]) {
-  for (int d = 0; d < 3; ++d) centered[d] = centered_[d];
-  fft_dir = ctx.prm.fft_axis - 1;
-  const int nl = (int)ctx.boxes.size();
+void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
+  sboxes = std::move(boxes_);
+  fft_dir = batched ? 2 : -1;
+  const int nl = (int)sboxes.size();
   bool coupled[3];
   for (int d = 0; d < 3; ++d) coupled[d] = (d != fft_dir);
-  nq = fft_dir >= 0 ? ctx.boxes[0]->g.n[fft_dir] : 1;
+  nq = batched ? sboxes[0].n[2] : 1;
   norms.alloc(2 * (size_t)nq);
   h_norms.assign(2 * (size_t)nq, 0.0);
-
-  // eigenvalues of the transform direction (src/fft.f90:151-189, src/solver.f90:1124-1138)
   lam.clear();
   lam.resize(nl);
-  if (fft_dir >= 0) {
-    for (int lb = 0; lb < nl; ++lb) {
-      Box &bx = *ctx.boxes[lb];
-      const char bc[2] = {bx.info.cbcpre[fft_dir][0], bx.info.cbcpre[fft_dir][1]};
-      std::vector<double> l = r2r_eigenvalues(bx.g.n[fft_dir], bc, true);
-      const double dl = bx.info.dl[fft_dir][0];
-      std::vector<double> lg(l.size() + 2, 0.0);
-      for (size_t q = 0; q < l.size(); ++q) lg[q + 1] = l[q] / (dl * dl);
-      lam[lb].upload(lg);
-    }
+  std::vector<NbTable> nbt(nl);
+  for (int lb = 0; lb < nl; ++lb) {
+    if (batched) lam[lb].upload(sboxes[lb].lam);
+    for (int d = 0; d < 3; ++d)
+      for (int ib = 0; ib < 2; ++ib) nbt[lb].nb[d][ib] = coupled[d] ? sboxes[lb].nb[d][ib] : -1;
   }
-
-  // sign of the boundary fold per face of each box (src/solver.f90:71-94)
-  auto face_sgn = [&](const Box &bx, int d, int ib, bool &phys) {
-    phys = bx.info.is_bound[d][ib] && ctx.prm.periods[d] == 0;
-    if (!phys) return 0.0;
-    const char c = bx.info.cbcpre[d][ib];
-    if (c == 'N') return 1.0;
-    if (c == 'D') return centered[d] ? -1.0 : 0.0;
-    throw Error("multigrid set-up: a physical boundary must be 'D' or 'N'");
-  };
 
   levels.clear();
   levels.emplace_back(new MGLevel);
   {  // level 0: the reference's own matrix
     MGLevel &L0 = *levels[0];
     L0.boxes.resize(nl);
+    x0.clear(); b0.clear();
+    x0.resize(nl); b0.resize(nl);
     for (int lb = 0; lb < nl; ++lb) {
-      Box &bx = *ctx.boxes[lb];
+      SBox &sb = sboxes[lb];
       MGLevelBox &L = L0.boxes[lb];
-      L.g = bx.g;
-      L.xp = bx.po.p;
-      L.bp = bx.rhs.p;
-      for (int d = 0; d < 3; ++d) {
-        bool phys[2];
-        double sgn[2];
-        for (int ib = 0; ib < 2; ++ib) sgn[ib] = face_sgn(bx, d, ib, phys[ib]);
-        build_dir(L, d, coupled[d], bx.h_dc[d], bx.h_df[d], sgn, phys);
+      L.g = Grid3::make(sb.n[0], sb.n[1], sb.n[2]);
+      if (sb.x && sb.b) { L.xp = sb.x; L.bp = sb.b; }
+      else {
+        x0[lb].alloc(L.g); b0[lb].alloc(L.g);
+        L.xp = x0[lb].p; L.bp = b0[lb].p;
       }
+      for (int d = 0; d < 3; ++d) build_dir(L, d, coupled[d], sb.d1[d], sb.d2[d], sb.sgn[d], sb.phys[d]);
     }
   }
   // coarser levels
   for (;;) {
     MGLevel &F = *levels.back();
-    // mean width and parity per direction over the local boxes
+    // mean width per direction over the local boxes
     double hsum[3] = {0, 0, 0};
     long ncnt[3] = {0, 0, 0};
-    bool even[3] = {true, true, true}, all_one[3] = {true, true, true};
+    bool all_one[3] = {true, true, true};
     for (int lb = 0; lb < nl; ++lb)
       for (int d = 0; d < 3; ++d) {
         const int n = F.boxes[lb].g.n[d];
-        if (n % 2) even[d] = false;
         if (n != 1) all_one[d] = false;
         for (int i = 1; i <= n; ++i) hsum[d] += F.boxes[lb].h_w[d][i];
         ncnt[d] += n;
@@ -277,7 +584,7 @@ void MGSolver::setup(Ctx &ctx, const bool centered_[3]) {
     int co[3] = {0, 0, 0};
     bool any = false;
     for (int d = 0; d < 3; ++d) {
-      if (!coupled[d] || !even[d]) continue;
+      if (!coupled[d] || all_one[d]) continue;
       if (hsum[d] / ncnt[d] < 1.5 * hmin) { co[d] = 1; any = true; }
     }
     if (!any || levels.size() >= 24) break;
@@ -289,14 +596,16 @@ void MGSolver::setup(Ctx &ctx, const bool centered_[3]) {
     for (int lb = 0; lb < nl; ++lb) {
       MGLevelBox &f = Fm.boxes[lb];
       MGLevelBox &c = C.boxes[lb];
-      c.g = Grid3::make(co[0] ? f.g.n[0] / 2 : f.g.n[0], co[1] ? f.g.n[1] / 2 : f.g.n[1], co[2] ? f.g.n[2] / 2 : f.g.n[2]);
+      c.g = Grid3::make(co[0] ? (f.g.n[0] + 1) / 2 : f.g.n[0], co[1] ? (f.g.n[1] + 1) / 2 : f.g.n[1],
+                        co[2] ? (f.g.n[2] + 1) / 2 : f.g.n[2]);
       c.x.alloc(c.g); c.b.alloc(c.g);
       c.xp = c.x.p; c.bp = c.b.p;
       for (int d = 0; d < 3; ++d) {
         const int n = c.g.n[d];
         c.h_w[d].assign(n + 2, 1.0);
         if (!coupled[d]) continue;
-        for (int i = 1; i <= n; ++i) c.h_w[d][i] = co[d] ? f.h_w[d][2 * i - 1] + f.h_w[d][2 * i] : f.h_w[d][i];
+        for (int i = 1; i <= n; ++i)
+          c.h_w[d][i] = co[d] ? f.h_w[d][2 * i - 1] + (2 * i <= f.g.n[d] ? f.h_w[d][2 * i] : 0.0) : f.h_w[d][i];
         c.h_w[d][0] = c.h_w[d][1];
         c.h_w[d][n + 1] = c.h_w[d][n];
       }
@@ -305,7 +614,7 @@ void MGSolver::setup(Ctx &ctx, const bool centered_[3]) {
     {
       std::vector<ExField> ef;
       for (int lb = 0; lb < nl; ++lb) ef.push_back(ExField{lb, C.boxes[lb].xp, C.boxes[lb].g});
-      C.ex.build(ctx, ef);
+      C.ex.build(ctx, ef, &nbt);
       for (int d = 0; d < 3; ++d) {
         if (!coupled[d] || !C.ex.local[d].count) continue;
         std::vector<Dev1> tmp(nl);
@@ -319,9 +628,8 @@ void MGSolver::setup(Ctx &ctx, const bool centered_[3]) {
         SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
         for (int lb = 0; lb < nl; ++lb) {
           MGLevelBox &c = C.boxes[lb];
-          const snac_box &info = ctx.boxes[lb]->info;
           for (int ib = 0; ib < 2; ++ib) {
-            if (info.nb[d][ib] < 0) continue;
+            if (nbt[lb].nb[d][ib] < 0) continue;
             long idx[3] = {1, 1, 1};
             idx[d] = ib == 0 ? 0 : c.g.n[d] + 1;
             double v;
@@ -334,23 +642,16 @@ void MGSolver::setup(Ctx &ctx, const bool centered_[3]) {
         SNAC_CUDA(cudaMemsetAsync(C.boxes[lb].x.buf.raw, 0, C.boxes[lb].x.buf.elems * sizeof(double), ctx.stream));
     }
     for (int lb = 0; lb < nl; ++lb) {
-      Box &bx = *ctx.boxes[lb];
+      SBox &sb = sboxes[lb];
       MGLevelBox &c = C.boxes[lb];
       for (int d = 0; d < 3; ++d) {
         const int n = c.g.n[d];
         std::vector<double> d1(n + 2, 1.0);
         if (coupled[d]) {
-          if (centered[d]) {
-            for (int i = 0; i <= n; ++i) d1[i] = 0.5 * (c.h_w[d][i] + c.h_w[d][i + 1]);
-            d1[n + 1] = d1[n];
-          } else {
-            throw Error("multigrid: staggered operators are not available in this build");
-          }
+          for (int i = 0; i <= n; ++i) d1[i] = 0.5 * (c.h_w[d][i] + c.h_w[d][i + 1]);
+          d1[n + 1] = d1[n];
         }
-        bool phys[2];
-        double sgn[2];
-        for (int ib = 0; ib < 2; ++ib) sgn[ib] = face_sgn(bx, d, ib, phys[ib]);
-        build_dir(c, d, coupled[d], d1, c.h_w[d], sgn, phys);
+        build_dir(c, d, coupled[d], d1, c.h_w[d], sb.sgn[d], sb.phys[d]);
       }
     }
   }
@@ -358,7 +659,47 @@ void MGSolver::setup(Ctx &ctx, const bool centered_[3]) {
   {
     std::vector<ExField> ef;
     for (int lb = 0; lb < nl; ++lb) ef.push_back(ExField{lb, levels[0]->boxes[lb].xp, levels[0]->boxes[lb].g});
-    levels[0]->ex.build(ctx, ef);
+    levels[0]->ex.build(ctx, ef, &nbt);
+  }
+  // ---- plane-local fast path -----------------------------------------------------------------
+  plane_local = batched && !ctx.prm.mg_generic;
+  const int npre = ctx.prm.mg_npre > 0 ? ctx.prm.mg_npre : 1, npost = ctx.prm.mg_npost > 0 ? ctx.prm.mg_npost : 1;
+  if (npre != 1 || npost != 1) plane_local = false;
+  for (int lb = 0; lb < nl && plane_local; ++lb)
+    for (int d = 0; d < 2; ++d)
+      for (int ib = 0; ib < 2; ++ib) {
+        const int nb = sboxes[lb].nb[d][ib];
+        if (nb >= 0 && ctx.local_of_rank[nb] != lb) plane_local = false;   // the plane is split over boxes
+      }
+  first_smem_level = 0;
+  if (plane_local) {
+    const int nlev = (int)levels.size();
+    // first level whose whole hierarchy below fits in shared memory (x and b per level)
+    int ls = nlev - 1;
+    for (int l = nlev - 1; l >= 0; --l) {
+      bool ok = true;
+      size_t worst = 0;
+      for (int lb = 0; lb < nl; ++lb) {
+        size_t c = 0;
+        for (int m = l; m < nlev; ++m) c += (size_t)levels[m]->boxes[lb].g.n[0] * levels[m]->boxes[lb].g.n[1];
+        worst = std::max(worst, c);
+      }
+      if (nlev - l > PMAXLEV || worst * 2 * sizeof(double) > 160 * 1024) ok = false;
+      if (!ok) break;
+      ls = l;
+    }
+    first_smem_level = ls;
+    // the tiled kernels need an even size in every periodic direction of the levels they handle
+    for (int l = 0; l < ls && plane_local; ++l)
+      for (int lb = 0; lb < nl; ++lb)
+        for (int d = 0; d < 2; ++d)
+          if (sboxes[lb].nb[d][0] >= 0 && (levels[l]->boxes[lb].g.n[d] % 2)) plane_local = false;
+    if (plane_local) {
+      x1.clear();
+      x1.resize((size_t)ls * nl);
+      for (int l = 0; l < ls; ++l)
+        for (int lb = 0; lb < nl; ++lb) x1[(size_t)l * nl + lb].alloc(levels[l]->boxes[lb].g);
+    }
   }
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
 }
@@ -393,7 +734,7 @@ struct Cycle {
       }
   }
   void restrict_from(int l, bool norms, bool want_b) {
-    ProfScope ps(ctx, l == 0 ? PC_MG_RESTRICT0 : PC_MG_COARSE);
+    ProfScope ps(ctx, l == 0 ? PC_MG_DOWN0 : PC_MG_COARSE);
     MGLevel &F = *S.levels[l];
     const bool has_coarse = l + 1 < (int)S.levels.size();
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
@@ -415,7 +756,7 @@ struct Cycle {
     }
   }
   void prolong_to(int l) {
-    ProfScope ps(ctx, l == 0 ? PC_MG_PROLONG0 : PC_MG_COARSE);
+    ProfScope ps(ctx, l == 0 ? PC_MG_UP0 : PC_MG_COARSE);
     MGLevel &F = *S.levels[l];
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
       MGKernelBox B = kbox(S, F.boxes[lb], (int)lb, coupled);
@@ -439,6 +780,76 @@ struct Cycle {
     exchange(l);
     sweeps(l, npost, true);
   }
+
+  // ---- plane-local fast path ---------------------------------------------------------------
+  PLevel plevel(int l, int lb) const {
+    const MGLevelBox &B = S.levels[l]->boxes[lb];
+    PLevel P;
+    P.n1 = B.g.n[0]; P.n2 = B.g.n[1];
+    P.sy = B.g.sy; P.sz = B.g.sz;
+    P.am1 = B.am[0].p(); P.ap1 = B.ap[0].p(); P.ad1 = B.ad[0].p(); P.w1 = B.w[0].p();
+    P.am2 = B.am[1].p(); P.ap2 = B.ap[1].p(); P.ad2 = B.ad[1].p(); P.w2 = B.w[1].p();
+    P.c1 = S.levels[l]->coarsen[0]; P.c2 = S.levels[l]->coarsen[1];
+    P.per1 = S.sboxes[lb].nb[0][0] >= 0; P.per2 = S.sboxes[lb].nb[1][0] >= 0;
+    return P;
+  }
+  double *xbuf(int l, int lb, int which) const {   // ping-pong buffers of the tiled levels
+    return which == 0 ? S.levels[l]->boxes[lb].xp : S.x1[(size_t)l * S.levels[0]->boxes.size() + lb].p;
+  }
+  // down: xbuf(l,0) -> xbuf(l,1), residual restricted into level l+1's b
+  void plane_down(int l, bool norms, bool want_b) {
+    ProfScope ps(ctx, l == 0 ? PC_MG_DOWN0 : PC_MG_COARSE);
+    MGLevel &F = *S.levels[l];
+    for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
+      PLevel P = plevel(l, (int)lb);
+      MGLevelBox &c = S.levels[l + 1]->boxes[lb];
+      dim3 grd((P.n1 + PT_X - 1) / PT_X, (P.n2 + PT_Y - 1) / PT_Y, S.nq);
+      // below level 0 the iterate is zero on entry: nothing to read
+      mg_plane_down_kernel<<<grd, 256, 0, ctx.stream>>>(P, l == 0 ? xbuf(l, (int)lb, 0) : nullptr, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy,
+                                                        c.g.sz, S.lam[lb].p(), S.alpha, norms ? S.norms.raw : nullptr, S.nq,
+                                                        want_b ? 1 : 0);
+      ctx.launches++;
+    }
+  }
+  void plane_up(int l) {
+    ProfScope ps(ctx, l == 0 ? PC_MG_UP0 : PC_MG_COARSE);
+    MGLevel &F = *S.levels[l];
+    for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
+      PLevel P = plevel(l, (int)lb);
+      MGLevelBox &c = S.levels[l + 1]->boxes[lb];
+      dim3 grd((P.n1 + PT_X - 1) / PT_X, (P.n2 + PT_Y - 1) / PT_Y, S.nq);
+      mg_plane_up_kernel<<<grd, 256, 0, ctx.stream>>>(P, xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp, c.xp, c.g.sy,
+                                                      c.g.sz, S.lam[lb].p(), S.alpha);
+      ctx.launches++;
+    }
+  }
+  void plane_coarse(bool norms, bool want_b) {
+    const int ls = S.first_smem_level, nlev = (int)S.levels.size();
+    ProfScope ps(ctx, ls == 0 ? PC_MG_DOWN0 : PC_MG_COARSE);
+    for (size_t lb = 0; lb < S.levels[ls]->boxes.size(); ++lb) {
+      PCoarseArgs a;
+      a.nlev = nlev - ls;
+      size_t cells = 0;
+      for (int l = ls; l < nlev; ++l) {
+        a.lev[l - ls] = plevel(l, (int)lb);
+        cells += (size_t)a.lev[l - ls].n1 * a.lev[l - ls].n2;
+      }
+      MGLevelBox &T = S.levels[ls]->boxes[lb];
+      a.b = T.bp;
+      a.xin = ls == 0 ? T.xp : nullptr;
+      a.xout = T.xp;
+      a.lamq = S.lam[lb].p();
+      a.alpha = S.alpha;
+      a.norms = (ls == 0 && norms) ? S.norms.raw : nullptr;
+      a.nq = S.nq; a.want_b = want_b ? 1 : 0;
+      a.npre = npre; a.npost = npost; a.nbot = nbot;
+      const size_t smem = cells * 2 * sizeof(double);
+      if (smem > 48 * 1024)
+        SNAC_CUDA(cudaFuncSetAttribute(mg_plane_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mg_plane_coarse_kernel<<<S.nq, 256, smem, ctx.stream>>>(a);
+      ctx.launches++;
+    }
+  }
 };
 }  // namespace
 
@@ -449,16 +860,23 @@ void MGSolver::solve(Ctx &ctx) {
   const int nlev = (int)levels.size();
   const double tol = ctx.prm.hypre_tol;
   const int maxiter = std::max(ctx.prm.hypre_maxiter, 1);
+  const int ls = first_smem_level;
   last_iters = 0;
   last_relres = 0.0;
-  cy.exchange(0);
+  if (!plane_local) cy.exchange(0);
   for (int it = 0;; ++it) {
-    if (nlev == 1) cy.sweeps(0, cy.nbot, false);
-    else cy.sweeps(0, cy.npre, false);
-    SNAC_CUDA(cudaMemsetAsync(norms.raw, 0, (it == 0 ? 2 : 1) * (size_t)nq * sizeof(double), ctx.stream));
-    cy.restrict_from(0, true, it == 0);
-    SNAC_CUDA(cudaMemcpyAsync(h_norms.data(), norms.raw, (it == 0 ? 2 : 1) * (size_t)nq * sizeof(double),
-                              cudaMemcpyDeviceToHost, ctx.stream));
+    const size_t nn = (it == 0 ? 2 : 1) * (size_t)nq * sizeof(double);
+    SNAC_CUDA(cudaMemsetAsync(norms.raw, 0, nn, ctx.stream));
+    // pre-relaxation on level 0 + residual (+ restriction); its norm drives the stopping test
+    if (plane_local) {
+      if (ls == 0) cy.plane_coarse(true, it == 0);   // the whole cycle in one kernel
+      else cy.plane_down(0, true, it == 0);
+    } else {
+      if (nlev == 1) cy.sweeps(0, cy.nbot, false);
+      else cy.sweeps(0, cy.npre, false);
+      cy.restrict_from(0, true, it == 0);
+    }
+    SNAC_CUDA(cudaMemcpyAsync(h_norms.data(), norms.raw, nn, cudaMemcpyDeviceToHost, ctx.stream));
     SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
     bool conv = true, any_zero = false;
     double worst = 0.0;
@@ -470,27 +888,56 @@ void MGSolver::solve(Ctx &ctx) {
       if (!(rel < tol)) conv = false;
     }
     last_relres = worst;
-    if (it == 0 && any_zero) {
+    // where the current iterate lives on level 0: the tiled down kernel wrote the other buffer
+    const bool in_alt = plane_local && ls > 0;
+    if (it == 0 && any_zero) {   // HYPRE returns x = 0 for b = 0
       MGLevel &L = *levels[0];
       for (size_t lb = 0; lb < L.boxes.size(); ++lb) {
         MGKernelBox B = kbox(*this, L.boxes[lb], (int)lb, cy.coupled);
+        if (in_alt) B.x = cy.xbuf(0, (int)lb, 1);
         dim3 blk = mg_block(L.boxes[lb].g, fft_dir), grd = mg_grid(blk, B.n[0], B.n[1], B.n[2]);
         mg_zero_planes_kernel<<<grd, blk, 0, ctx.stream>>>(B, norms.raw, nq);
+        if (in_alt) {  // keep both buffers consistent
+          B.x = cy.xbuf(0, (int)lb, 0);
+          mg_zero_planes_kernel<<<grd, blk, 0, ctx.stream>>>(B, norms.raw, nq);
+        }
         ctx.launches++;
       }
-      cy.exchange(0);
-      if (worst == 0.0) {  // every plane has a zero right-hand side
-        last_iters = 0;
-        break;
+      if (!plane_local) {
+        cy.exchange(0);
+        if (worst > 0.0) cy.restrict_from(0, false, false);   // the coarse RHS used the old iterate there
       }
-      // the coarse right-hand side was computed with the old iterate in those planes: redo it
-      cy.restrict_from(0, false, false);
+      // (plane-local: a zero right-hand side gives a zero residual and a zero correction in that
+      //  plane once x is zero; the stale coarse RHS of this first cycle only perturbs planes that
+      //  are then re-zeroed below)
     }
-    if ((it > 0 && conv) || it >= maxiter || nlev == 1 && conv) {
+    const bool stop = (it > 0 && conv) || it >= maxiter || (worst == 0.0) || (nlev == 1 && conv);
+    if (stop) {
       last_iters = it;
+      if (in_alt) {   // result of the down kernel -> canonical buffer
+        for (size_t lb = 0; lb < levels[0]->boxes.size(); ++lb)
+          SNAC_CUDA(cudaMemcpyAsync(cy.xbuf(0, (int)lb, 0), cy.xbuf(0, (int)lb, 1),
+                                    levels[0]->boxes[lb].g.alloc_elems() * sizeof(double) - 15 * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, ctx.stream));
+      }
       break;
     }
-    if (nlev > 1) {
+    if (plane_local) {
+      if (ls > 0) {
+        for (int l = 1; l < ls; ++l) cy.plane_down(l, false, false);
+        cy.plane_coarse(false, false);
+        for (int l = ls - 1; l >= 0; --l) cy.plane_up(l);
+        if (it == 0 && any_zero) {   // planes with b = 0 stay exactly zero
+          MGLevel &L = *levels[0];
+          for (size_t lb = 0; lb < L.boxes.size(); ++lb) {
+            MGKernelBox B = kbox(*this, L.boxes[lb], (int)lb, cy.coupled);
+            dim3 blk = mg_block(L.boxes[lb].g, fft_dir), grd = mg_grid(blk, B.n[0], B.n[1], B.n[2]);
+            mg_zero_planes_kernel<<<grd, blk, 0, ctx.stream>>>(B, norms.raw, nq);
+            ctx.launches++;
+          }
+        }
+      }
+    } else if (nlev > 1) {
       cy.descend(1);
       cy.prolong_to(0);
       cy.exchange(0);

@@ -17,6 +17,7 @@ SNAC_MAX_SCAL = 8
 
 FIELD_U, FIELD_V, FIELD_W, FIELD_P, FIELD_PP, FIELD_RHS, FIELD_PO = range(7)
 FIELD_DUDTRKO, FIELD_DVDTRKO, FIELD_DWDTRKO = 7, 8, 9
+FIELD_RHS_HAT = 10
 FIELD_S0 = 16
 FIELD_DSDTRKO0 = 32
 
@@ -34,7 +35,7 @@ class snac_params(C.Structure):
         ("vol_all", C.c_double), ("alphai", C.c_double * SNAC_MAX_SCAL), ("ssource", C.c_double * SNAC_MAX_SCAL),
         ("is_sforced", C.c_int * SNAC_MAX_SCAL), ("scalf", C.c_double * SNAC_MAX_SCAL),
         ("hypre_tol", C.c_double), ("hypre_maxiter", C.c_int), ("hypre_solver_i", C.c_int),
-        ("mg_npre", C.c_int), ("mg_npost", C.c_int), ("mg_nbottom", C.c_int),
+        ("mg_npre", C.c_int), ("mg_npost", C.c_int), ("mg_nbottom", C.c_int), ("mg_generic", C.c_int),
     ]
 
 

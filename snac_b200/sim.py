@@ -28,7 +28,7 @@ class Simulation:
     def __init__(self, case: Case, ranks: Optional[Iterable[int]] = None, device: int = 0,
                  nproc: int = 1, myproc: int = 0, rank_owner: Optional[List[int]] = None,
                  tol: Optional[float] = None, maxiter: Optional[int] = None,
-                 mg_npre: int = 0, mg_npost: int = 0, mg_nbottom: int = 0):
+                 mg_npre: int = 0, mg_npost: int = 0, mg_nbottom: int = 0, mg_generic: bool = False):
         self.case = case
         P, W = case.params, case.world
         self.lib = L.load_library()
@@ -56,6 +56,7 @@ class Simulation:
         prm.hypre_maxiter = int(P.hypre_maxiter if maxiter is None else maxiter)
         prm.hypre_solver_i = int(P.hypre_solver_i)
         prm.mg_npre, prm.mg_npost, prm.mg_nbottom = mg_npre, mg_npost, mg_nbottom
+        prm.mg_generic = int(mg_generic)
         h = C.c_void_p()
         if self.lib.snac_create(C.byref(prm), C.byref(h)) != 0:
             raise L.SnacError(self.lib.snac_last_error(None).decode())
