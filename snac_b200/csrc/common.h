@@ -219,6 +219,7 @@ struct MGLevelBox {
   Field3 x, b;                 // x is owned except on level 0 where it may alias a context field
   double *xp = nullptr, *bp = nullptr;
   Dev1 am[3], ap[3], ad[3], w[3];   // ghosted 1-D coefficient arrays (index 0..n+1)
+  Dev1 sam[3], sap[3], se[3], srw[3];  // scaled by the cell width: am/w, ap/w, ad/w, 1/w
   std::vector<double> h_w[3];       // host copy of cell widths (for coarsening)
 };
 

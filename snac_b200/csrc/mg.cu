@@ -27,6 +27,7 @@
 // cell per box and direction.
 #include <algorithm>
 #include <cmath>
+#include <math_constants.h>
 
 #include "common.h"
 
@@ -169,126 +170,193 @@ struct PLevel {
   int n1, n2;
   long sy, sz;        // row / plane strides of this level's global arrays
   const double *am1, *ap1, *ad1, *w1, *am2, *ap2, *ad2, *w2;  // ghosted, index 1..n
+  const double *sam1, *sap1, *se1, *srw1, *sam2, *sap2, *se2, *srw2;  // am/w, ap/w, ad/w, 1/w
   int c1, c2;         // coarsening towards the next level
   int per1, per2;     // periodic wrap onto the box itself
 };
 
-constexpr int PT_X = 64, PT_Y = 32;     // tile interior
+// Tile geometry: 64 columns including the halo, stored split by colour so that each lane owns one
+// column pair (2k, 2k+1) and every shared-memory access of a sweep is stride-1 across the warp;
+// a warp works on two rows at a time (so that the column parity of a colour is a compile-time
+// constant), the 8 warps of a CTA on row pairs 16 apart.
+constexpr int PW = 64, PHW = PW / 2;
+constexpr int PT_Y = 32;                // interior rows of a tile
 constexpr int PH_D = 3, PH_U = 2;       // halo of the down / up kernels
+__host__ __device__ constexpr int ptx(int H) { return PW - 2 * H; }   // interior columns of a tile
 
-__device__ inline int wrap1(int g, int n) {  // 1-based periodic wrap, valid for -n < g <= 2n
-  return g < 1 ? g + n : (g > n ? g - n : g);
+__device__ inline int wrapn(int g, int n) {  // 1-based periodic wrap
+  int r = (g - 1) % n;
+  if (r < 0) r += n;
+  return r + 1;
 }
 
-// loads the tile of x (and b) and the 1-D coefficients; cells outside a non-periodic domain get
-// zero values and zero coefficients (they are never updated)
+// The cell equations are used in the scaled form (division by w1*w2):
+//   x = ( b/(w1 w2) - (a1m xL + a1p xR + a2m xD + a2p xU) ) / (e1 + e2 + lambda)
+// with a = am/w, e = ad/w precomputed per level on the host (PLevel::s*).  Cells outside a
+// non-periodic domain get a = 0 and e = +inf, so that "updating" them yields exactly 0 without a
+// branch; halo cells too close to the tile edge are updated with incomplete data, which is
+// harmless because nothing that is kept reads them.
 template <int H>
-__device__ inline void ptile_load(const PLevel &L, const double *x, const double *b, long qoff, int i0, int j0,
-                                  double *sx, double *sb, double *c1, double *c2) {
-  constexpr int W = PT_X + 2 * H, Ht = PT_Y + 2 * H;
-  for (int t = threadIdx.x; t < W; t += blockDim.x) {
-    const int gu = i0 + t - H;
+struct PTileSmem {
+  static constexpr int HT = PT_Y + 2 * H;
+  double x[2][HT][PHW];
+  double b[2][HT][PHW];
+  double ram[HT], rap[HT], re[HT], rw[HT], rrw[HT];
+  int rgj[HT];   // global row index, 0: outside the domain
+};
+
+struct PCols {   // the two columns (ti = 2*lane, 2*lane+1) owned by a lane; e includes lambda
+  double am0, am1, ap0, ap1, e0, e1, w0, w1, rw0, rw1;
+  int gi0, gi1;  // global column index, 0: outside the domain
+};
+
+template <int H>
+__device__ inline void pt_setup(const PLevel &L, int i0, int j0, double lam, PCols &C, PTileSmem<H> &S) {
+  constexpr int HT = PT_Y + 2 * H;
+  const int lane = threadIdx.x & 31;
+  auto col = [&](int sft, double &am, double &ap, double &e, double &w, double &rw, int &gi) {
+    const int gu = i0 + 2 * lane + sft - H;
     const bool ok = L.per1 || (gu >= 1 && gu <= L.n1);
-    const int gi = L.per1 ? wrap1(gu, L.n1) : gu;
-    c1[t] = ok ? __ldg(L.am1 + gi) : 0.0; c1[W + t] = ok ? __ldg(L.ap1 + gi) : 0.0;
-    c1[2 * W + t] = ok ? __ldg(L.ad1 + gi) : 0.0; c1[3 * W + t] = ok ? __ldg(L.w1 + gi) : 0.0;
-  }
-  for (int t = threadIdx.x; t < Ht; t += blockDim.x) {
+    gi = ok ? (L.per1 ? wrapn(gu, L.n1) : gu) : 0;
+    am = ok ? __ldg(L.sam1 + gi) : 0.0; ap = ok ? __ldg(L.sap1 + gi) : 0.0;
+    e = ok ? __ldg(L.se1 + gi) + lam : CUDART_INF;
+    w = ok ? __ldg(L.w1 + gi) : 0.0; rw = ok ? __ldg(L.srw1 + gi) : 0.0;
+  };
+  col(0, C.am0, C.ap0, C.e0, C.w0, C.rw0, C.gi0);
+  col(1, C.am1, C.ap1, C.e1, C.w1, C.rw1, C.gi1);
+  for (int t = threadIdx.x; t < HT; t += blockDim.x) {
     const int gv = j0 + t - H;
     const bool ok = L.per2 || (gv >= 1 && gv <= L.n2);
-    const int gj = L.per2 ? wrap1(gv, L.n2) : gv;
-    c2[t] = ok ? __ldg(L.am2 + gj) : 0.0; c2[Ht + t] = ok ? __ldg(L.ap2 + gj) : 0.0;
-    c2[2 * Ht + t] = ok ? __ldg(L.ad2 + gj) : 0.0; c2[3 * Ht + t] = ok ? __ldg(L.w2 + gj) : 0.0;
-  }
-  for (int t = threadIdx.x; t < W * Ht; t += blockDim.x) {
-    const int ti = t % W, tj = t / W;
-    const int gu = i0 + ti - H, gv = j0 + tj - H;
-    const bool ok = (L.per1 || (gu >= 1 && gu <= L.n1)) && (L.per2 || (gv >= 1 && gv <= L.n2));
-    double vx = 0.0, vb = 0.0;
-    if (ok) {
-      const int gi = L.per1 ? wrap1(gu, L.n1) : gu, gj = L.per2 ? wrap1(gv, L.n2) : gv;
-      const long o = qoff + gi + L.sy * gj;
-      vx = x ? x[o] : 0.0;
-      vb = b[o];
-    }
-    sx[t] = vx;
-    sb[t] = vb;
+    const int gj = ok ? (L.per2 ? wrapn(gv, L.n2) : gv) : 0;
+    S.rgj[t] = gj;
+    S.ram[t] = ok ? __ldg(L.sam2 + gj) : 0.0; S.rap[t] = ok ? __ldg(L.sap2 + gj) : 0.0;
+    S.re[t] = ok ? __ldg(L.se2 + gj) : CUDART_INF;
+    S.rw[t] = ok ? __ldg(L.w2 + gj) : 0.0; S.rrw[t] = ok ? __ldg(L.srw2 + gj) : 0.0;
   }
 }
 
-// one colour of a Gauss-Seidel sweep on the tile cells whose ring index is >= ring
-template <int H>
-__device__ inline void ptile_sweep(const PLevel &L, int i0, int j0, int color, int ring, double *sx, const double *sb,
-                                   const double *c1, const double *c2, double lam) {
-  constexpr int W = PT_X + 2 * H, Ht = PT_Y + 2 * H;
-  const int wi = W - 2 * ring, hj = Ht - 2 * ring;
-  const int half = wi / 2;  // W is even
-  for (int t = threadIdx.x; t < half * hj; t += blockDim.x) {
-    const int tj = ring + t / half;
-    const int gv = j0 + tj - H;
-    // first cell of this colour in the row: parity of (gu + gv) with gu = i0 + ti - H
-    int ti = ring + 2 * (t % half);
-    if (((i0 + ti - H + gv) & 1) != color) ti += 1;
-    const int gu = i0 + ti - H;
-    if (!((L.per1 || (gu >= 1 && gu <= L.n1)) && (L.per2 || (gv >= 1 && gv <= L.n2)))) continue;
-    const double w1 = c1[3 * W + ti], w2 = c2[3 * Ht + tj];
-    const double diag = w2 * c1[2 * W + ti] + w1 * c2[2 * Ht + tj] + lam * w1 * w2;
-    if (diag == 0.0) continue;
-    const int c = ti + W * tj;
-    const double off = w2 * (c1[ti] * sx[c - 1] + c1[W + ti] * sx[c + 1]) + w1 * (c2[tj] * sx[c - W] + c2[Ht + tj] * sx[c + W]);
-    sx[c] = (sb[c] - off) / diag;
+// update of the cell (row tj, column 2*lane + SFT) of colour COLOR
+template <int H, int COLOR, int SFT>
+__device__ __forceinline__ void pt_update(PTileSmem<H> &S, const PCols &C, int tj, int lane) {
+  const double *xo = &S.x[1 - COLOR][0][0];
+  const int c = tj * PHW + lane;
+  const double am = SFT ? C.am1 : C.am0, ap = SFT ? C.ap1 : C.ap0, e = SFT ? C.e1 : C.e0;
+  const double off = am * xo[c - 1 + SFT] + ap * xo[c + SFT] + S.ram[tj] * xo[c - PHW] + S.rap[tj] * xo[c + PHW];
+  S.x[COLOR][tj][lane] = (S.b[COLOR][tj][lane] - off) * __drcp_rn(e + S.re[tj]);
+}
+
+// one colour of a Gauss-Seidel sweep on rows RING .. HT-RING-1 (all columns, see above)
+template <int H, int RING, int COLOR>
+__device__ __forceinline__ void pt_sweep(PTileSmem<H> &S, const PCols &C) {
+  constexpr int HT = PT_Y + 2 * H;
+  constexpr int S0 = (COLOR + RING) & 1;   // column parity of this colour in row RING
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int tj = RING + 2 * warp; tj < HT - RING; tj += 16) {
+    pt_update<H, COLOR, S0>(S, C, tj, lane);
+    if (tj + 1 < HT - RING) pt_update<H, COLOR, 1 - S0>(S, C, tj + 1, lane);
   }
 }
 
 __global__ void __launch_bounds__(256) mg_plane_down_kernel(const PLevel L, const double *xin, double *xout, const double *b,
                                                             double *cb, long csy, long csz, const double *lamq, double alpha,
                                                             double *norms, int nq, int want_b) {
-  constexpr int H = PH_D, W = PT_X + 2 * H, Ht = PT_Y + 2 * H;
-  __shared__ double sx[W * Ht], sb[W * Ht], c1[4 * W], c2[4 * Ht];
+  constexpr int H = PH_D, HT = PT_Y + 2 * H, TX = ptx(H);
+  static_assert(H == 3, "the fused restriction assumes an odd halo width");
+  __shared__ PTileSmem<H> S;
+  __shared__ double red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = blockIdx.z;
-  const int i0 = 1 + blockIdx.x * PT_X, j0 = 1 + blockIdx.y * PT_Y;
+  const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * PT_Y;
   const long qoff = (long)(q + 1) * L.sz;
   const double lam = alpha + __ldg(lamq + q + 1);
-  ptile_load<H>(L, xin, b, qoff, i0, j0, sx, sb, c1, c2);
+  PCols C;
+  pt_setup<H>(L, i0, j0, lam, C, S);
   __syncthreads();
-  ptile_sweep<H>(L, i0, j0, 0, 1, sx, sb, c1, c2, lam);
-  __syncthreads();
-  ptile_sweep<H>(L, i0, j0, 1, 2, sx, sb, c1, c2, lam);
-  __syncthreads();
-  // residual on the interior (into sb), new x to global
   double r2 = 0.0, b2 = 0.0;
-  for (int t = threadIdx.x; t < PT_X * PT_Y; t += blockDim.x) {
-    const int ti = H + t % PT_X, tj = H + t / PT_X;
-    const int gu = i0 + ti - H, gv = j0 + tj - H;
-    const int c = ti + W * tj;
-    double r = 0.0;
-    if (gu <= L.n1 && gv <= L.n2) {
-      const double w1 = c1[3 * W + ti], w2 = c2[3 * Ht + tj];
-      const double diag = w2 * c1[2 * W + ti] + w1 * c2[2 * Ht + tj] + lam * w1 * w2;
-      const double off = w2 * (c1[ti] * sx[c - 1] + c1[W + ti] * sx[c + 1]) + w1 * (c2[tj] * sx[c - W] + c2[Ht + tj] * sx[c + W]);
-      const double bb = sb[c];
-      r = bb - (diag * sx[c] + off);
-      r2 += r * r;
-      b2 += bb * bb;
-      xout[qoff + gu + L.sy * gv] = sx[c];
+  // load x and the scaled right-hand side, split by colour
+  for (int tj = warp; tj < HT; tj += 8) {
+    const int gj = S.rgj[tj];
+    const double rrw = S.rrw[tj];
+    const bool rin = tj >= H && tj < H + PT_Y && (j0 + tj - H) <= L.n2;
+    const long orow = qoff + L.sy * gj;
+    double v0 = 0.0, v1 = 0.0, b0 = 0.0, b1 = 0.0;
+    if (gj > 0) {
+      if (C.gi0 > 0) { if (xin) v0 = xin[orow + C.gi0]; b0 = b[orow + C.gi0]; }
+      if (C.gi1 > 0) { if (xin) v1 = xin[orow + C.gi1]; b1 = b[orow + C.gi1]; }
     }
-    sb[c] = r;   // each cell is read and written by the same thread only
+    if (rin) {
+      if (2 * lane >= H && 2 * lane < PW - H && (i0 + 2 * lane - H) <= L.n1) b2 += b0 * b0;
+      if (2 * lane + 1 >= H && 2 * lane + 1 < PW - H && (i0 + 2 * lane + 1 - H) <= L.n1) b2 += b1 * b1;
+    }
+    const int c0 = tj & 1;   // colour of column 2*lane in this row
+    S.x[c0][tj][lane] = v0; S.b[c0][tj][lane] = b0 * (C.rw0 * rrw);
+    S.x[1 - c0][tj][lane] = v1; S.b[1 - c0][tj][lane] = b1 * (C.rw1 * rrw);
   }
   __syncthreads();
-  // restriction: sum of the children's residuals
-  if (cb) {
-    const int cw = L.c1 ? PT_X / 2 : PT_X, ch = L.c2 ? PT_Y / 2 : PT_Y;
-    const int cn1 = L.c1 ? (L.n1 + 1) / 2 : L.n1, cn2 = L.c2 ? (L.n2 + 1) / 2 : L.n2;
+  pt_sweep<H, 1, 0>(S, C);
+  __syncthreads();
+  pt_sweep<H, 2, 1>(S, C);
+  __syncthreads();
+  // new iterate to global memory, residual (non-zero on colour 0 only) and its restriction
+  const bool full = L.c1 && L.c2;
+  const int cn1 = L.c1 ? (L.n1 + 1) / 2 : L.n1, cn2 = L.c2 ? (L.n2 + 1) / 2 : L.n2;
+  for (int tj = H + 2 * warp; tj < H + PT_Y; tj += 16) {   // tj is odd: (tj, tj+1) are the children rows of a coarse row
+    double resA = 0.0, resB = 0.0;   // residual at (tj, column 2*lane+1) and at (tj+1, column 2*lane)
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr) {
+      const int t = tj + dr, gv = j0 + t - H;
+      const bool rin = gv <= L.n2;
+      const int gu0 = i0 + 2 * lane - H, gu1 = gu0 + 1;
+      const bool in0 = rin && 2 * lane >= H && 2 * lane < PW - H && gu0 <= L.n1;
+      const bool in1 = rin && 2 * lane + 1 >= H && 2 * lane + 1 < PW - H && gu1 <= L.n1;
+      const int c0 = t & 1;
+      const long orow = qoff + L.sy * gv;
+      if (in0) xout[orow + gu0] = S.x[c0][t][lane];
+      if (in1) xout[orow + gu1] = S.x[1 - c0][t][lane];
+      // colour-0 cell of this row: column parity = row parity (dr = 0: odd row -> column 2*lane+1)
+      const double *xo = &S.x[1][0][0];
+      const int c = t * PHW + lane;
+      if (dr == 0) {
+        if (in1) {
+          const double off = C.am1 * xo[c] + C.ap1 * xo[c + 1] + S.ram[t] * xo[c - PHW] + S.rap[t] * xo[c + PHW];
+          resA = (S.b[0][t][lane] - off - (C.e1 + S.re[t]) * S.x[0][t][lane]) * (C.w1 * S.rw[t]);
+        }
+      } else {
+        if (in0) {
+          const double off = C.am0 * xo[c - 1] + C.ap0 * xo[c] + S.ram[t] * xo[c - PHW] + S.rap[t] * xo[c + PHW];
+          resB = (S.b[0][t][lane] - off - (C.e0 + S.re[t]) * S.x[0][t][lane]) * (C.w0 * S.rw[t]);
+        }
+      }
+    }
+    r2 += resA * resA + resB * resB;
+    if (full) {
+      // coarse cell = columns (2*lane+1, 2*lane+2) x rows (tj, tj+1): its colour-0 children are
+      // (tj, 2*lane+1) on this lane and (tj+1, 2*lane+2) on the next one
+      const double nxt = __shfl_down_sync(0xffffffffu, resB, 1);
+      const int I = (i0 - 1) / 2 + lane, J = (j0 + tj - H + 1) / 2;
+      if (cb && lane >= 1 && lane <= (PW - H - 2) / 2 && I <= cn1 && J <= cn2)
+        cb[(long)(q + 1) * csz + I + csy * J] = resA + nxt;
+    } else {
+      S.b[0][tj][lane] = resA;       // (tj odd: colour 0 sits in column 2*lane+1; tj+1: column 2*lane)
+      S.b[0][tj + 1][lane] = resB;
+    }
+  }
+  if (!full && cb) {   // semi-coarsening: generic restriction through shared memory
+    __syncthreads();
+    const int cw = L.c1 ? TX / 2 : TX, ch = L.c2 ? PT_Y / 2 : PT_Y;
     const int I0 = L.c1 ? (i0 + 1) / 2 : i0, J0 = L.c2 ? (j0 + 1) / 2 : j0;
     for (int t = threadIdx.x; t < cw * ch; t += blockDim.x) {
       const int ci = t % cw, cj = t / cw;
       const int I = I0 + ci, J = J0 + cj;
       if (I > cn1 || J > cn2) continue;
       const int ti0 = H + (L.c1 ? 2 * ci : ci), tj0 = H + (L.c2 ? 2 * cj : cj);
-      double s = 0.0;
+      double sum = 0.0;
       for (int dj = 0; dj <= L.c2; ++dj)
-        for (int di = 0; di <= L.c1; ++di) s += sb[(ti0 + di) + W * (tj0 + dj)];  // cells past the domain hold r = 0
-      cb[(long)(q + 1) * csz + I + csy * J] = s;
+        for (int di = 0; di <= L.c1; ++di) {
+          const int ti = ti0 + di, tj = tj0 + dj;
+          if (((ti + tj) & 1) == 0) sum += S.b[0][tj][ti >> 1];
+        }
+      cb[(long)(q + 1) * csz + I + csy * J] = sum;
     }
   }
   if (norms) {
@@ -296,11 +364,10 @@ __global__ void __launch_bounds__(256) mg_plane_down_kernel(const PLevel L, cons
       r2 += __shfl_xor_sync(0xffffffffu, r2, o);
       b2 += __shfl_xor_sync(0xffffffffu, b2, o);
     }
-    __shared__ double red[2][8];
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = r2; red[1][threadIdx.x >> 5] = b2; }
+    if (lane == 0) { red[0][warp] = r2; red[1][warp] = b2; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { r2 += red[0][w]; b2 += red[1][w]; }
+      for (int w = 1; w < 8; ++w) { r2 += red[0][w]; b2 += red[1][w]; }
       atomicAdd(norms + q, r2);
       if (want_b) atomicAdd(norms + nq + q, b2);
     }
@@ -310,31 +377,45 @@ __global__ void __launch_bounds__(256) mg_plane_down_kernel(const PLevel L, cons
 __global__ void __launch_bounds__(256) mg_plane_up_kernel(const PLevel L, const double *xin, double *xout, const double *b,
                                                           const double *cx, long csy, long csz, const double *lamq,
                                                           double alpha) {
-  constexpr int H = PH_U, W = PT_X + 2 * H, Ht = PT_Y + 2 * H;
-  __shared__ double sx[W * Ht], sb[W * Ht], c1[4 * W], c2[4 * Ht];
+  constexpr int H = PH_U, HT = PT_Y + 2 * H, TX = ptx(H);
+  __shared__ PTileSmem<H> S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = blockIdx.z;
-  const int i0 = 1 + blockIdx.x * PT_X, j0 = 1 + blockIdx.y * PT_Y;
-  const long qoff = (long)(q + 1) * L.sz;
+  const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * PT_Y;
+  const long qoff = (long)(q + 1) * L.sz, cqoff = (long)(q + 1) * csz;
   const double lam = alpha + __ldg(lamq + q + 1);
-  ptile_load<H>(L, xin, b, qoff, i0, j0, sx, sb, c1, c2);
-  // coarse-grid correction (piecewise constant prolongation)
-  for (int t = threadIdx.x; t < W * Ht; t += blockDim.x) {
-    const int ti = t % W, tj = t / W;
-    const int gu = i0 + ti - H, gv = j0 + tj - H;
-    if (!((L.per1 || (gu >= 1 && gu <= L.n1)) && (L.per2 || (gv >= 1 && gv <= L.n2)))) continue;
-    const int gi = L.per1 ? wrap1(gu, L.n1) : gu, gj = L.per2 ? wrap1(gv, L.n2) : gv;
-    const int I = L.c1 ? (gi + 1) >> 1 : gi, J = L.c2 ? (gj + 1) >> 1 : gj;
-    sx[t] += __ldg(cx + (long)(q + 1) * csz + I + csy * J);   // same thread loaded sx[t]
+  PCols C;
+  pt_setup<H>(L, i0, j0, lam, C, S);
+  __syncthreads();
+  // load x + coarse-grid correction (piecewise-constant prolongation) and the scaled right-hand side
+  const int I0 = L.c1 ? (C.gi0 + 1) >> 1 : C.gi0, I1 = L.c1 ? (C.gi1 + 1) >> 1 : C.gi1;
+  for (int tj = warp; tj < HT; tj += 8) {
+    const int gj = S.rgj[tj];
+    const double rrw = S.rrw[tj];
+    const long orow = qoff + L.sy * gj;
+    const long crow = cqoff + csy * (L.c2 ? (gj + 1) >> 1 : gj);
+    double v0 = 0.0, v1 = 0.0, b0 = 0.0, b1 = 0.0;
+    if (gj > 0) {
+      if (C.gi0 > 0) { v0 = xin[orow + C.gi0] + __ldg(cx + crow + I0); b0 = b[orow + C.gi0]; }
+      if (C.gi1 > 0) { v1 = xin[orow + C.gi1] + __ldg(cx + crow + I1); b1 = b[orow + C.gi1]; }
+    }
+    const int c0 = tj & 1;
+    S.x[c0][tj][lane] = v0; S.b[c0][tj][lane] = b0 * (C.rw0 * rrw);
+    S.x[1 - c0][tj][lane] = v1; S.b[1 - c0][tj][lane] = b1 * (C.rw1 * rrw);
   }
   __syncthreads();
-  ptile_sweep<H>(L, i0, j0, 1, 1, sx, sb, c1, c2, lam);
+  pt_sweep<H, 1, 1>(S, C);
   __syncthreads();
-  ptile_sweep<H>(L, i0, j0, 0, 2, sx, sb, c1, c2, lam);
+  pt_sweep<H, 2, 0>(S, C);
   __syncthreads();
-  for (int t = threadIdx.x; t < PT_X * PT_Y; t += blockDim.x) {
-    const int ti = H + t % PT_X, tj = H + t / PT_X;
-    const int gu = i0 + ti - H, gv = j0 + tj - H;
-    if (gu <= L.n1 && gv <= L.n2) xout[qoff + gu + L.sy * gv] = sx[ti + W * tj];
+  for (int tj = H + warp; tj < H + PT_Y; tj += 8) {
+    const int gv = j0 + tj - H;
+    if (gv > L.n2) continue;
+    const int gu0 = i0 + 2 * lane - H, gu1 = gu0 + 1;
+    const int c0 = tj & 1;
+    const long orow = qoff + L.sy * gv;
+    if (2 * lane >= H && 2 * lane < PW - H && gu0 <= L.n1) xout[orow + gu0] = S.x[c0][tj][lane];
+    if (2 * lane + 1 >= H && 2 * lane + 1 < PW - H && gu1 <= L.n1) xout[orow + gu1] = S.x[1 - c0][tj][lane];
   }
 }
 
@@ -525,6 +606,12 @@ static void build_dir(MGLevelBox &L, int d, bool coupled, const std::vector<doub
   }
   L.h_w[d] = w;
   L.am[d].upload(am); L.ap[d].upload(ap); L.ad[d].upload(ad); L.w[d].upload(w);
+  std::vector<double> sam(n + 2, 0.0), sap(n + 2, 0.0), se(n + 2, 0.0), srw(n + 2, 1.0);
+  for (int i = 1; i <= n; ++i) {
+    srw[i] = 1.0 / w[i];
+    sam[i] = am[i] * srw[i]; sap[i] = ap[i] * srw[i]; se[i] = ad[i] * srw[i];
+  }
+  L.sam[d].upload(sam); L.sap[d].upload(sap); L.se[d].upload(se); L.srw[d].upload(srw);
 }
 
 void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
@@ -789,6 +876,8 @@ struct Cycle {
     P.sy = B.g.sy; P.sz = B.g.sz;
     P.am1 = B.am[0].p(); P.ap1 = B.ap[0].p(); P.ad1 = B.ad[0].p(); P.w1 = B.w[0].p();
     P.am2 = B.am[1].p(); P.ap2 = B.ap[1].p(); P.ad2 = B.ad[1].p(); P.w2 = B.w[1].p();
+    P.sam1 = B.sam[0].p(); P.sap1 = B.sap[0].p(); P.se1 = B.se[0].p(); P.srw1 = B.srw[0].p();
+    P.sam2 = B.sam[1].p(); P.sap2 = B.sap[1].p(); P.se2 = B.se[1].p(); P.srw2 = B.srw[1].p();
     P.c1 = S.levels[l]->coarsen[0]; P.c2 = S.levels[l]->coarsen[1];
     P.per1 = S.sboxes[lb].nb[0][0] >= 0; P.per2 = S.sboxes[lb].nb[1][0] >= 0;
     return P;
@@ -803,7 +892,7 @@ struct Cycle {
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
       PLevel P = plevel(l, (int)lb);
       MGLevelBox &c = S.levels[l + 1]->boxes[lb];
-      dim3 grd((P.n1 + PT_X - 1) / PT_X, (P.n2 + PT_Y - 1) / PT_Y, S.nq);
+      dim3 grd((P.n1 + ptx(PH_D) - 1) / ptx(PH_D), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
       // below level 0 the iterate is zero on entry: nothing to read
       mg_plane_down_kernel<<<grd, 256, 0, ctx.stream>>>(P, l == 0 ? xbuf(l, (int)lb, 0) : nullptr, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy,
                                                         c.g.sz, S.lam[lb].p(), S.alpha, norms ? S.norms.raw : nullptr, S.nq,
@@ -817,7 +906,7 @@ struct Cycle {
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
       PLevel P = plevel(l, (int)lb);
       MGLevelBox &c = S.levels[l + 1]->boxes[lb];
-      dim3 grd((P.n1 + PT_X - 1) / PT_X, (P.n2 + PT_Y - 1) / PT_Y, S.nq);
+      dim3 grd((P.n1 + ptx(PH_U) - 1) / ptx(PH_U), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
       mg_plane_up_kernel<<<grd, 256, 0, ctx.stream>>>(P, xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp, c.xp, c.g.sy,
                                                       c.g.sz, S.lam[lb].p(), S.alpha);
       ctx.launches++;
