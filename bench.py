@@ -182,7 +182,7 @@ def main():
     iters = []
     for _ in range(args.steps):
         g.step()
-        iters.append(g.solver_stats()[0])
+        iters.append(g.solver_mean_iters())
     g.lib.snac_timer_stop(g.h, C.byref(ms))
     barrier()
     launches = g.launch_count() - l0

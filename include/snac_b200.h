@@ -144,6 +144,9 @@ SNAC_API int snac_step(snac_handle *h, double dt);
 /* iterations and worst relative residual of the most recent linear solve (the reference ignores
  * HYPRE's ierr and iteration counts, src/solver.f90:553-556; non-convergence is not an error). */
 SNAC_API int snac_solver_stats(snac_handle *h, int *iters, double *relres);
+/* V-cycles of the most recent solve averaged over the independent 2-D problems (wavenumbers): each
+ * one stops on its own residual, as the reference's one-solve-per-wavenumber loop does */
+SNAC_API int snac_solver_mean_iters(snac_handle *h, double *mean_iters);
 /* Per-kernel-class device timing.  While enabled, every class section is bracketed by CUDA events
  * on the handle's stream and waited for, so the stream is serialised: use it to attribute time, not
  * to measure throughput.  Classes are numbered from 0; snac_profile_name returns NULL past the end. */

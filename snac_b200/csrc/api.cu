@@ -520,8 +520,7 @@ int snac_step(snac_handle *h, double dt) {
 
 int snac_solver_stats(snac_handle *h, int *iters, double *relres) {
   SNAC_TRY(h, {
-    if (iters) *iters = h->ctx.psolver.last_iters;
-    if (relres) *relres = h->ctx.psolver.last_relres;
+    h->ctx.psolver.stats(h->ctx, iters, relres, nullptr);
   })
 }
 int snac_profile_enable(snac_handle *h, int on) {
@@ -552,6 +551,9 @@ int snac_timer_stop(snac_handle *h, double *ms) {
     SNAC_CUDA(cudaEventElapsedTime(&f, h->ctx.timer_ev[0], h->ctx.timer_ev[1]));
     if (ms) *ms = f;
   })
+}
+int snac_solver_mean_iters(snac_handle *h, double *mean_iters) {
+  SNAC_TRY(h, h->ctx.psolver.stats(h->ctx, nullptr, nullptr, mean_iters))
 }
 long long snac_launch_count(const snac_handle *h) { return h ? h->ctx.launches : -1; }
 int snac_sync(snac_handle *h) { SNAC_TRY(h, SNAC_CUDA(cudaStreamSynchronize(h->ctx.stream))) }

@@ -264,9 +264,14 @@ struct MGSolver {
   int nq = 1;                      // number of independent planes (wavenumbers)
   DevBuf norms;                    // [2*nq]: sum r^2, sum b^2 per plane
   std::vector<double> h_norms;
+  bool use_tiles = false;
   bool plane_local = false;        // fused shared-memory path (planes not split over boxes)
   int first_smem_level = 0;        // first level handled by the one-CTA-per-plane kernel
   std::vector<Field3> x1;          // second x buffer of the tiled levels [level*nbox + box]
+  int *d_active = nullptr, *d_where = nullptr, *d_iters = nullptr, *d_count = nullptr;  // per-plane stopping flags
+  int *h_count = nullptr;          // pinned
+  double last_mean_iters = 0.0;
+  void stats(Ctx &ctx, int *iters, double *relres, double *mean_iters);
   int last_iters = 0;
   double last_relres = 0.0;
   double alpha = 0.0;              // extra diagonal shift (IMPDIFF: alphai)

@@ -259,13 +259,14 @@ __device__ __forceinline__ void pt_sweep(PTileSmem<H> &S, const PCols &C) {
 
 __global__ void __launch_bounds__(256) mg_plane_down_kernel(const PLevel L, const double *xin, double *xout, const double *b,
                                                             double *cb, long csy, long csz, const double *lamq, double alpha,
-                                                            double *norms, int nq, int want_b) {
+                                                            double *norms, int nq, int want_b, const int *active) {
   constexpr int H = PH_D, HT = PT_Y + 2 * H, TX = ptx(H);
   static_assert(H == 3, "the fused restriction assumes an odd halo width");
   __shared__ PTileSmem<H> S;
   __shared__ double red[2][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = blockIdx.z;
+  if (active && !active[q]) return;   // this wavenumber has converged
   const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * PT_Y;
   const long qoff = (long)(q + 1) * L.sz;
   const double lam = alpha + __ldg(lamq + q + 1);
@@ -376,11 +377,12 @@ __global__ void __launch_bounds__(256) mg_plane_down_kernel(const PLevel L, cons
 
 __global__ void __launch_bounds__(256) mg_plane_up_kernel(const PLevel L, const double *xin, double *xout, const double *b,
                                                           const double *cx, long csy, long csz, const double *lamq,
-                                                          double alpha) {
+                                                          double alpha, const int *active) {
   constexpr int H = PH_U, HT = PT_Y + 2 * H, TX = ptx(H);
   __shared__ PTileSmem<H> S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = blockIdx.z;
+  if (active && !active[q]) return;
   const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * PT_Y;
   const long qoff = (long)(q + 1) * L.sz, cqoff = (long)(q + 1) * csz;
   const double lam = alpha + __ldg(lamq + q + 1);
@@ -419,6 +421,240 @@ __global__ void __launch_bounds__(256) mg_plane_up_kernel(const PLevel L, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-marching variants of the two fused kernels.  A warp owns 64 columns (two per lane) and
+// marches over the rows of its chunk, keeping a window of six rows in registers; the horizontal
+// neighbours of a cell are the lane's other column or one warp shuffle away, the vertical ones are
+// other window slots, so the stencil needs no shared memory and no block-level barrier.  Row t is
+// loaded one step ahead; at step t the first colour of row t-1, the second colour of row t-2 and
+// the output (store, residual, restriction) of row t-3 (down) / t-2 (up) are done.
+// ------------------------------------------------------------------------------------------
+constexpr int MRY = 32;   // interior rows marched by one warp
+
+struct MCols {            // per-lane column data (columns 2*lane, 2*lane+1 of the warp's strip)
+  double am0, am1, ap0, ap1, e0, e1, w0, w1, rw0, rw1;
+  int gi0, gi1;
+};
+
+template <int H>
+__device__ __forceinline__ void march_cols(const PLevel &L, int i0, double lam, int lane, MCols &C) {
+  auto col = [&](int sft, double &am, double &ap, double &e, double &w, double &rw, int &gi) {
+    const int gu = i0 + 2 * lane + sft - H;
+    const bool ok = L.per1 || (gu >= 1 && gu <= L.n1);
+    gi = ok ? (L.per1 ? wrapn(gu, L.n1) : gu) : 0;
+    am = ok ? __ldg(L.sam1 + gi) : 0.0; ap = ok ? __ldg(L.sap1 + gi) : 0.0;
+    e = ok ? __ldg(L.se1 + gi) + lam : CUDART_INF;
+    w = ok ? __ldg(L.w1 + gi) : 0.0; rw = ok ? __ldg(L.srw1 + gi) : 0.0;
+  };
+  col(0, C.am0, C.ap0, C.e0, C.w0, C.rw0, C.gi0);
+  col(1, C.am1, C.ap1, C.e1, C.w1, C.rw1, C.gi1);
+}
+
+// per-warp row table in shared memory: [0] a2m, [1] a2p, [2] e2, [3] w2, [4] 1/w2, [5] global row (as double; 0: outside)
+template <int H>
+__device__ __forceinline__ void march_rows(const PLevel &L, int j0, int lane, double (*rt)[MRY + 2 * H]) {
+  constexpr int HT = MRY + 2 * H;
+  for (int t = lane; t < HT; t += 32) {
+    const int gv = j0 + t - H;
+    const bool ok = L.per2 || (gv >= 1 && gv <= L.n2);
+    const int gj = ok ? (L.per2 ? wrapn(gv, L.n2) : gv) : 0;
+    rt[0][t] = ok ? __ldg(L.sam2 + gj) : 0.0; rt[1][t] = ok ? __ldg(L.sap2 + gj) : 0.0;
+    rt[2][t] = ok ? __ldg(L.se2 + gj) : CUDART_INF;
+    rt[3][t] = ok ? __ldg(L.w2 + gj) : 0.0; rt[4][t] = ok ? __ldg(L.srw2 + gj) : 0.0;
+    rt[5][t] = (double)gj;
+  }
+  __syncwarp();
+}
+
+// Gauss-Seidel update of one cell.  A: the cell is in column 2*lane (else 2*lane+1); xs/xo: this
+// row's own-column and other-column values; xm/xp: the own column one row below/above.
+#define MARCH_UPD(A, xs, xo, xm, xp, bs, r)                                                        \
+  {                                                                                                 \
+    const double l_ = (A) ? __shfl_up_sync(0xffffffffu, xo, 1) : xo;                                \
+    const double r_ = (A) ? xo : __shfl_down_sync(0xffffffffu, xo, 1);                              \
+    const double off_ = ((A) ? C.am0 : C.am1) * l_ + ((A) ? C.ap0 : C.ap1) * r_ + rt[0][r] * (xm) + rt[1][r] * (xp); \
+    xs = ((bs) - off_) * __drcp_rn(((A) ? C.e0 : C.e1) + rt[2][r]);                                 \
+  }
+
+__global__ void __launch_bounds__(256) mg_march_down_kernel(const PLevel L, const double *__restrict__ xin, double *__restrict__ xout,
+                                                            const double *__restrict__ b, double *__restrict__ cb, long csy, long csz,
+                                                            const double *lamq, double alpha, double *norms, int nq, int want_b,
+                                                            int ntx, int nty, const int *active) {
+  constexpr int H = 3, HT = MRY + 2 * H, TX = PW - 2 * H;
+  __shared__ double rtab[8][6][HT];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long wid = (long)blockIdx.x * 8 + wib;
+  const int tx = (int)(wid % ntx), ty = (int)((wid / ntx) % nty), q = (int)(wid / ((long)ntx * nty));
+  if (q >= nq || (active && !active[q])) return;
+  double (*rt)[HT] = rtab[wib];
+  const int i0 = 1 + tx * TX, j0 = 1 + ty * MRY;
+  const long qoff = (long)(q + 1) * L.sz;
+  const double lam = alpha + __ldg(lamq + q + 1);
+  MCols C;
+  march_cols<H>(L, i0, lam, lane, C);
+  march_rows<H>(L, j0, lane, rt);
+  const bool cin0 = 2 * lane >= H && 2 * lane < PW - H && (i0 + 2 * lane - H) <= L.n1;          // column kept by this warp
+  const bool cin1 = 2 * lane + 1 >= H && 2 * lane + 1 < PW - H && (i0 + 2 * lane + 1 - H) <= L.n1;
+  const int gu0 = i0 + 2 * lane - H;
+  const int cn1 = L.c1 ? (L.n1 + 1) / 2 : L.n1, cn2 = L.c2 ? (L.n2 + 1) / 2 : L.n2;
+  const int Ic = (i0 - 1) / 2 + lane;   // coarse column of the pair (2*lane+1, 2*lane+2) when c1
+  const bool cpair = lane >= 1 && lane <= (PW - H - 2) / 2 && Ic <= cn1;
+  const long cq = (long)(q + 1) * csz;
+  double xa[6], xb[6], ba[6], bb[6];
+  double r2 = 0.0, b2 = 0.0, resA = 0.0;
+
+#define MARCH_LOAD(t, S)                                                                           \
+  {                                                                                                 \
+    const int gj_ = (int)rt[5][t];                                                                  \
+    double v0_ = 0.0, v1_ = 0.0, b0_ = 0.0, b1_ = 0.0;                                              \
+    if (gj_ > 0) {                                                                                  \
+      const long o_ = qoff + L.sy * gj_;                                                            \
+      if (C.gi0 > 0) { if (xin) v0_ = xin[o_ + C.gi0]; b0_ = b[o_ + C.gi0]; }                       \
+      if (C.gi1 > 0) { if (xin) v1_ = xin[o_ + C.gi1]; b1_ = b[o_ + C.gi1]; }                       \
+    }                                                                                               \
+    if (want_b && (t) >= H && (t) < H + MRY && (j0 + (t) - H) <= L.n2)                              \
+      b2 += (cin0 ? b0_ * b0_ : 0.0) + (cin1 ? b1_ * b1_ : 0.0);                                    \
+    const double s_ = rt[4][t];                                                                     \
+    xa[S] = v0_; xb[S] = v1_; ba[S] = b0_ * (C.rw0 * s_); bb[S] = b1_ * (C.rw1 * s_);               \
+  }
+
+  // one step: K = t mod 6 (so that window slots and the row parity are compile-time constants)
+#define MARCH_DOWN_STEP(K)                                                                          \
+  if (t0 + (K) < HT + 0) {                                                                          \
+    const int t = t0 + (K);                                                                         \
+    if (t + 1 < HT) MARCH_LOAD(t + 1, ((K) + 1) % 6)                                                \
+    if (t >= 2) { /* colour 0 of row t-1 (slot K+5): column 2*lane in even rows */                  \
+      constexpr int R = ((K) + 5) % 6, Rm = ((K) + 4) % 6, Rp = (K);                                \
+      if ((((K) + 1) & 1) == 0) MARCH_UPD(1, xa[R], xb[R], xa[Rm], xa[Rp], ba[R], t - 1)            \
+      else MARCH_UPD(0, xb[R], xa[R], xb[Rm], xb[Rp], bb[R], t - 1)                                 \
+    }                                                                                               \
+    if (t >= 4) { /* colour 1 of row t-2 (slot K+4): column 2*lane+1 in even rows */                \
+      constexpr int R = ((K) + 4) % 6, Rm = ((K) + 3) % 6, Rp = ((K) + 5) % 6;                      \
+      if (((K) & 1) == 0) MARCH_UPD(0, xb[R], xa[R], xb[Rm], xb[Rp], bb[R], t - 2)                  \
+      else MARCH_UPD(1, xa[R], xb[R], xa[Rm], xa[Rp], ba[R], t - 2)                                 \
+    }                                                                                               \
+    if (t >= 2 * H) { /* output of row t-3 (slot K+3) */                                            \
+      constexpr int R = ((K) + 3) % 6, Rm = ((K) + 2) % 6, Rp = ((K) + 4) % 6;                      \
+      const int r = t - 3, gv = j0 + r - H;                                                         \
+      const bool rin = gv <= L.n2;                                                                  \
+      const long o = qoff + L.sy * gv;                                                              \
+      if (rin && cin0) xout[o + gu0] = xa[R];                                                       \
+      if (rin && cin1) xout[o + gu0 + 1] = xb[R];                                                   \
+      if ((((K) + 1) & 1) == 1) { /* odd row: colour 0 in column 2*lane+1 */                        \
+        const double rgt = __shfl_down_sync(0xffffffffu, xa[R], 1);                                 \
+        double res = (bb[R] - (C.am1 * xa[R] + C.ap1 * rgt + rt[0][r] * xb[Rm] + rt[1][r] * xb[Rp]) - \
+                      (C.e1 + rt[2][r]) * xb[R]) * (C.w1 * rt[3][r]);                               \
+        if (!(rin && cin1)) res = 0.0;                                                              \
+        r2 += res * res;                                                                            \
+        resA = res;                                                                                 \
+        if (cb && L.c1 && !L.c2 && cpair && gv <= cn2) cb[cq + Ic + csy * gv] = res;                \
+      } else { /* even row: colour 0 in column 2*lane */                                            \
+        const double lft = __shfl_up_sync(0xffffffffu, xb[R], 1);                                   \
+        double res = (ba[R] - (C.am0 * lft + C.ap0 * xb[R] + rt[0][r] * xa[Rm] + rt[1][r] * xa[Rp]) - \
+                      (C.e0 + rt[2][r]) * xa[R]) * (C.w0 * rt[3][r]);                               \
+        if (!(rin && cin0)) res = 0.0;                                                              \
+        r2 += res * res;                                                                            \
+        if (cb) {                                                                                   \
+          const int J = (gv + 1) >> 1;   /* (gv-1, gv) are the children rows of coarse row J */     \
+          if (L.c1) {                                                                               \
+            const double nxt = __shfl_down_sync(0xffffffffu, res, 1);                               \
+            if (L.c2) { if (cpair && J <= cn2) cb[cq + Ic + csy * J] = resA + nxt; }                \
+            else if (cpair && gv <= cn2) cb[cq + Ic + csy * gv] = nxt;                              \
+          } else if (L.c2 && J <= cn2) {                                                            \
+            if (cin0) cb[cq + gu0 + csy * J] = res;                                                 \
+            if (cin1) cb[cq + gu0 + 1 + csy * J] = resA;                                            \
+          }                                                                                         \
+        }                                                                                           \
+      }                                                                                             \
+    }                                                                                               \
+  }
+
+  MARCH_LOAD(0, 0)
+  for (int t0 = 0; t0 < HT; t0 += 6) {
+    MARCH_DOWN_STEP(0) MARCH_DOWN_STEP(1) MARCH_DOWN_STEP(2) MARCH_DOWN_STEP(3) MARCH_DOWN_STEP(4) MARCH_DOWN_STEP(5)
+  }
+#undef MARCH_DOWN_STEP
+#undef MARCH_LOAD
+  if (norms) {
+    for (int o = 16; o > 0; o >>= 1) {
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    }
+    if (lane == 0) {
+      atomicAdd(norms + q, r2);
+      if (want_b) atomicAdd(norms + nq + q, b2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) mg_march_up_kernel(const PLevel L, const double *__restrict__ xin, double *__restrict__ xout,
+                                                          const double *__restrict__ b, const double *__restrict__ cx, long csy,
+                                                          long csz, const double *lamq, double alpha, int nq, int ntx, int nty,
+                                                          const int *active) {
+  constexpr int H = 2, HT = MRY + 2 * H, TX = PW - 2 * H;
+  __shared__ double rtab[8][6][HT];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long wid = (long)blockIdx.x * 8 + wib;
+  const int tx = (int)(wid % ntx), ty = (int)((wid / ntx) % nty), q = (int)(wid / ((long)ntx * nty));
+  if (q >= nq || (active && !active[q])) return;
+  double (*rt)[HT] = rtab[wib];
+  const int i0 = 1 + tx * TX, j0 = 1 + ty * MRY;
+  const long qoff = (long)(q + 1) * L.sz, cq = (long)(q + 1) * csz;
+  const double lam = alpha + __ldg(lamq + q + 1);
+  MCols C;
+  march_cols<H>(L, i0, lam, lane, C);
+  march_rows<H>(L, j0, lane, rt);
+  const bool cin0 = 2 * lane >= H && 2 * lane < PW - H && (i0 + 2 * lane - H) <= L.n1;
+  const bool cin1 = 2 * lane + 1 >= H && 2 * lane + 1 < PW - H && (i0 + 2 * lane + 1 - H) <= L.n1;
+  const int gu0 = i0 + 2 * lane - H;
+  const int I0 = L.c1 ? (C.gi0 + 1) >> 1 : C.gi0, I1 = L.c1 ? (C.gi1 + 1) >> 1 : C.gi1;
+  double xa[6], xb[6], ba[6], bb[6];
+
+#define MARCH_LOAD(t, S)                                                                           \
+  {                                                                                                 \
+    const int gj_ = (int)rt[5][t];                                                                  \
+    double v0_ = 0.0, v1_ = 0.0, b0_ = 0.0, b1_ = 0.0;                                              \
+    if (gj_ > 0) {                                                                                  \
+      const long o_ = qoff + L.sy * gj_;                                                            \
+      const long c_ = cq + csy * (L.c2 ? (gj_ + 1) >> 1 : gj_);                                     \
+      if (C.gi0 > 0) { v0_ = xin[o_ + C.gi0] + __ldg(cx + c_ + I0); b0_ = b[o_ + C.gi0]; }          \
+      if (C.gi1 > 0) { v1_ = xin[o_ + C.gi1] + __ldg(cx + c_ + I1); b1_ = b[o_ + C.gi1]; }          \
+    }                                                                                               \
+    const double s_ = rt[4][t];                                                                     \
+    xa[S] = v0_; xb[S] = v1_; ba[S] = b0_ * (C.rw0 * s_); bb[S] = b1_ * (C.rw1 * s_);               \
+  }
+
+#define MARCH_UP_STEP(K)                                                                            \
+  if (t0 + (K) < HT + 0) {                                                                          \
+    const int t = t0 + (K);                                                                         \
+    if (t + 1 < HT) MARCH_LOAD(t + 1, ((K) + 1) % 6)                                                \
+    if (t >= 2) { /* colour 1 of row t-1: column 2*lane+1 in even rows */                           \
+      constexpr int R = ((K) + 5) % 6, Rm = ((K) + 4) % 6, Rp = (K);                                \
+      if ((((K) + 1) & 1) == 0) MARCH_UPD(0, xb[R], xa[R], xb[Rm], xb[Rp], bb[R], t - 1)            \
+      else MARCH_UPD(1, xa[R], xb[R], xa[Rm], xa[Rp], ba[R], t - 1)                                 \
+    }                                                                                               \
+    if (t >= 4) { /* colour 0 of row t-2: column 2*lane in even rows; then the row is final */      \
+      constexpr int R = ((K) + 4) % 6, Rm = ((K) + 3) % 6, Rp = ((K) + 5) % 6;                      \
+      if (((K) & 1) == 0) MARCH_UPD(1, xa[R], xb[R], xa[Rm], xa[Rp], ba[R], t - 2)                  \
+      else MARCH_UPD(0, xb[R], xa[R], xb[Rm], xb[Rp], bb[R], t - 2)                                 \
+      const int r = t - 2, gv = j0 + r - H;                                                         \
+      if (r < H + MRY && gv <= L.n2) {                                                              \
+        const long o = qoff + L.sy * gv;                                                            \
+        if (cin0) xout[o + gu0] = xa[R];                                                            \
+        if (cin1) xout[o + gu0 + 1] = xb[R];                                                        \
+      }                                                                                             \
+    }                                                                                               \
+  }
+
+  MARCH_LOAD(0, 0)
+  for (int t0 = 0; t0 < HT; t0 += 6) {
+    MARCH_UP_STEP(0) MARCH_UP_STEP(1) MARCH_UP_STEP(2) MARCH_UP_STEP(3) MARCH_UP_STEP(4) MARCH_UP_STEP(5)
+  }
+#undef MARCH_UP_STEP
+#undef MARCH_LOAD
+}
+#undef MARCH_UPD
+
 // ---- whole coarse part of the V-cycle in shared memory: one CTA per wavenumber ----------------
 constexpr int PMAXLEV = 16;
 struct PCoarseArgs {
@@ -432,21 +668,24 @@ struct PCoarseArgs {
   double *norms;         // only when the top level is level 0
   int nq, want_b;
   int npre, npost, nbot;
+  const int *active;
 };
 
 __device__ inline void pc_sweep(const PLevel &L, double *x, const double *b, int color, double lam) {
-  const int n1 = L.n1, n2 = L.n2;
-  for (int t = threadIdx.x; t < n1 * n2; t += blockDim.x) {
-    const int i = t % n1 + 1, j = t / n1 + 1;
-    if (((i + j) & 1) != color) continue;
+  const int n1 = L.n1, n2 = L.n2, h1 = (n1 + 1) >> 1;
+  for (int t = threadIdx.x; t < h1 * n2; t += blockDim.x) {   // only the cells of this colour
+    const int j = t / h1 + 1;
+    const int i = 2 * (t % h1) + 2 - ((color + j) & 1);
+    if (i > n1) continue;
     const double w1 = __ldg(L.w1 + i), w2 = __ldg(L.w2 + j);
     const double diag = w2 * __ldg(L.ad1 + i) + w1 * __ldg(L.ad2 + j) + lam * w1 * w2;
     if (diag == 0.0) continue;
     const int im = i > 1 ? i - 1 : (L.per1 ? n1 : 1), ip = i < n1 ? i + 1 : (L.per1 ? 1 : n1);
     const int jm = j > 1 ? j - 1 : (L.per2 ? n2 : 1), jp = j < n2 ? j + 1 : (L.per2 ? 1 : n2);
+    const int c = (i - 1) + n1 * (j - 1);
     const double off = w2 * (__ldg(L.am1 + i) * x[(im - 1) + n1 * (j - 1)] + __ldg(L.ap1 + i) * x[(ip - 1) + n1 * (j - 1)]) +
                        w1 * (__ldg(L.am2 + j) * x[(i - 1) + n1 * (jm - 1)] + __ldg(L.ap2 + j) * x[(i - 1) + n1 * (jp - 1)]);
-    x[t] = (b[t] - off) / diag;
+    x[c] = (b[c] - off) * __drcp_rn(diag);
   }
   __syncthreads();
 }
@@ -462,9 +701,10 @@ __device__ inline double pc_resid(const PLevel &L, const double *x, const double
   return b[(i - 1) + n1 * (j - 1)] - (diag * x[(i - 1) + n1 * (j - 1)] + off);
 }
 
-__global__ void __launch_bounds__(256) mg_plane_coarse_kernel(const PCoarseArgs a) {
+__global__ void __launch_bounds__(512) mg_plane_coarse_kernel(const PCoarseArgs a) {
   extern __shared__ double sm[];
   const int q = blockIdx.x;
+  if (a.active && !a.active[q]) return;
   const double lam = a.alpha + __ldg(a.lamq + q + 1);
   // shared-memory layout: x_l, b_l for every level
   double *xs[PMAXLEV], *bs[PMAXLEV];
@@ -514,7 +754,7 @@ __global__ void __launch_bounds__(256) mg_plane_coarse_kernel(const PCoarseArgs 
   {
     const int l = a.nlev - 1;
     const PLevel &B = a.lev[l];
-    const int ns = (a.nlev == 1) ? a.nbot : a.nbot;
+    const int ns = min(a.nbot, B.n1 * B.n2);   // a 1 x 1 level is solved by one update
     for (int s = 0; s < ns; ++s) { pc_sweep(B, xs[l], bs[l], 0, lam); pc_sweep(B, xs[l], bs[l], 1, lam); }
     if (a.nlev == 1 && a.norms) {
       for (int t = threadIdx.x; t < B.n1 * B.n2; t += blockDim.x) {
@@ -546,7 +786,7 @@ __global__ void __launch_bounds__(256) mg_plane_coarse_kernel(const PCoarseArgs 
       r2 += __shfl_xor_sync(0xffffffffu, r2, o);
       b2 += __shfl_xor_sync(0xffffffffu, b2, o);
     }
-    __shared__ double red[2][8];
+    __shared__ double red[2][16];
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = r2; red[1][threadIdx.x >> 5] = b2; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -555,6 +795,49 @@ __global__ void __launch_bounds__(256) mg_plane_coarse_kernel(const PCoarseArgs 
       if (a.want_b) atomicAdd(a.norms + a.nq + q, b2);
     }
   }
+}
+
+// ---- per-wavenumber stopping test on the device ------------------------------------------------
+// norms = [sum r^2 | sum b^2 | relative residual] per plane.  A plane leaves the iteration when its
+// relative residual (after pre-relaxation, as in PFMG) is below the tolerance (from the second
+// cycle on), when its right-hand side is zero (x = 0), or at maxiter; the kernels of later cycles
+// skip it.  where[q]: 0 result in the main x buffer, 1 in the second buffer, 2 identically zero.
+__global__ void mg_flags_init_kernel(int *active, int *where, int *iters, int *count, int nq) {
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) { active[q] = 1; where[q] = 0; iters[q] = 0; }
+  if (threadIdx.x == 0) *count = nq;
+}
+
+__global__ void mg_flags_kernel(double *norms, int nq, double tol2, int it, int maxiter, int in_alt, int *active, int *where,
+                                int *iters, int *count) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    if (!active[q]) continue;
+    const double r2 = norms[q], b2 = norms[nq + q];
+    int act = 1;
+    if (b2 == 0.0) {
+      act = 0; where[q] = 2; iters[q] = 0; norms[2 * nq + q] = 0.0;
+    } else {
+      const double rel2 = r2 / b2;
+      norms[2 * nq + q] = sqrt(rel2);
+      iters[q] = it;
+      if ((it > 0 && rel2 < tol2) || it >= maxiter) { act = 0; where[q] = in_alt ? 1 : 0; }
+    }
+    active[q] = act;
+    if (act) { atomicAdd(&cnt, 1); norms[q] = 0.0; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *count = cnt;
+}
+
+__global__ void mg_finalize_kernel(double *x0, const double *x1, long sy, long sz, int n1, int n2, const int *where) {
+  const int q = blockIdx.z, w = where[q];
+  if (w == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > n1 || j > n2) return;
+  const long o = (long)(q + 1) * sz + i + sy * j;
+  x0[o] = (w == 1) ? x1[o] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -621,8 +904,14 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
   bool coupled[3];
   for (int d = 0; d < 3; ++d) coupled[d] = (d != fft_dir);
   nq = batched ? sboxes[0].n[2] : 1;
-  norms.alloc(2 * (size_t)nq);
+  norms.alloc(3 * (size_t)nq);
   h_norms.assign(2 * (size_t)nq, 0.0);
+  if (!d_active) {
+    SNAC_CUDA(cudaMalloc(&d_active, (3 * (size_t)nq + 4) * sizeof(int)));
+    d_where = d_active + nq; d_iters = d_where + nq; d_count = d_iters + nq;
+    SNAC_CUDA(cudaMemset(d_active, 0, (3 * (size_t)nq + 4) * sizeof(int)));
+    SNAC_CUDA(cudaMallocHost(&h_count, sizeof(int)));
+  }
   lam.clear();
   lam.resize(nl);
   std::vector<NbTable> nbt(nl);
@@ -750,6 +1039,7 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
   }
   // ---- plane-local fast path -----------------------------------------------------------------
   plane_local = batched && !ctx.prm.mg_generic;
+  use_tiles = getenv("SNAC_MG_MARCH") == nullptr;   // A/B switch: SNAC_MG_MARCH selects the register-marching kernels
   const int npre = ctx.prm.mg_npre > 0 ? ctx.prm.mg_npre : 1, npost = ctx.prm.mg_npost > 0 ? ctx.prm.mg_npost : 1;
   if (npre != 1 || npost != 1) plane_local = false;
   for (int lb = 0; lb < nl && plane_local; ++lb)
@@ -759,6 +1049,8 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
         if (nb >= 0 && ctx.local_of_rank[nb] != lb) plane_local = false;   // the plane is split over boxes
       }
   first_smem_level = 0;
+  // largest plane handed to the one-CTA-per-plane kernel (it is latency-bound: keep its top level small)
+  const size_t smem_cells = getenv("SNAC_MG_SMEM_CELLS") ? (size_t)atol(getenv("SNAC_MG_SMEM_CELLS")) : 2048;
   if (plane_local) {
     const int nlev = (int)levels.size();
     // first level whose whole hierarchy below fits in shared memory (x and b per level)
@@ -771,7 +1063,9 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
         for (int m = l; m < nlev; ++m) c += (size_t)levels[m]->boxes[lb].g.n[0] * levels[m]->boxes[lb].g.n[1];
         worst = std::max(worst, c);
       }
-      if (nlev - l > PMAXLEV || worst * 2 * sizeof(double) > 160 * 1024) ok = false;
+      size_t top = 0;
+      for (int lb = 0; lb < nl; ++lb) top = std::max(top, (size_t)levels[l]->boxes[lb].g.n[0] * levels[l]->boxes[lb].g.n[1]);
+      if (nlev - l > PMAXLEV || worst * 2 * sizeof(double) > 160 * 1024 || (l < nlev - 1 && top > smem_cells)) ok = false;
       if (!ok) break;
       ls = l;
     }
@@ -892,11 +1186,18 @@ struct Cycle {
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
       PLevel P = plevel(l, (int)lb);
       MGLevelBox &c = S.levels[l + 1]->boxes[lb];
-      dim3 grd((P.n1 + ptx(PH_D) - 1) / ptx(PH_D), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
-      // below level 0 the iterate is zero on entry: nothing to read
-      mg_plane_down_kernel<<<grd, 256, 0, ctx.stream>>>(P, l == 0 ? xbuf(l, (int)lb, 0) : nullptr, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy,
-                                                        c.g.sz, S.lam[lb].p(), S.alpha, norms ? S.norms.raw : nullptr, S.nq,
-                                                        want_b ? 1 : 0);
+      const double *xi = l == 0 ? xbuf(l, (int)lb, 0) : nullptr;   // below level 0 the iterate is zero on entry
+      if (S.use_tiles) {
+        dim3 grd((P.n1 + ptx(PH_D) - 1) / ptx(PH_D), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
+        mg_plane_down_kernel<<<grd, 256, 0, ctx.stream>>>(P, xi, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy, c.g.sz,
+                                                          S.lam[lb].p(), S.alpha, norms ? S.norms.raw : nullptr, S.nq, want_b ? 1 : 0, S.d_active);
+      } else {
+        const int ntx = (P.n1 + ptx(3) - 1) / ptx(3), nty = (P.n2 + MRY - 1) / MRY;
+        const long nw = (long)ntx * nty * S.nq;
+        mg_march_down_kernel<<<(unsigned)((nw + 7) / 8), 256, 0, ctx.stream>>>(P, xi, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy,
+                                                                              c.g.sz, S.lam[lb].p(), S.alpha,
+                                                                              norms ? S.norms.raw : nullptr, S.nq, want_b ? 1 : 0, ntx, nty, S.d_active);
+      }
       ctx.launches++;
     }
   }
@@ -906,9 +1207,16 @@ struct Cycle {
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
       PLevel P = plevel(l, (int)lb);
       MGLevelBox &c = S.levels[l + 1]->boxes[lb];
-      dim3 grd((P.n1 + ptx(PH_U) - 1) / ptx(PH_U), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
-      mg_plane_up_kernel<<<grd, 256, 0, ctx.stream>>>(P, xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp, c.xp, c.g.sy,
-                                                      c.g.sz, S.lam[lb].p(), S.alpha);
+      if (S.use_tiles) {
+        dim3 grd((P.n1 + ptx(PH_U) - 1) / ptx(PH_U), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
+        mg_plane_up_kernel<<<grd, 256, 0, ctx.stream>>>(P, xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp, c.xp, c.g.sy,
+                                                        c.g.sz, S.lam[lb].p(), S.alpha, S.d_active);
+      } else {
+        const int ntx = (P.n1 + ptx(2) - 1) / ptx(2), nty = (P.n2 + MRY - 1) / MRY;
+        const long nw = (long)ntx * nty * S.nq;
+        mg_march_up_kernel<<<(unsigned)((nw + 7) / 8), 256, 0, ctx.stream>>>(P, xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp,
+                                                                            c.xp, c.g.sy, c.g.sz, S.lam[lb].p(), S.alpha, S.nq, ntx, nty, S.d_active);
+      }
       ctx.launches++;
     }
   }
@@ -932,39 +1240,104 @@ struct Cycle {
       a.norms = (ls == 0 && norms) ? S.norms.raw : nullptr;
       a.nq = S.nq; a.want_b = want_b ? 1 : 0;
       a.npre = npre; a.npost = npost; a.nbot = nbot;
+      a.active = S.d_active;
       const size_t smem = cells * 2 * sizeof(double);
       if (smem > 48 * 1024)
         SNAC_CUDA(cudaFuncSetAttribute(mg_plane_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      mg_plane_coarse_kernel<<<S.nq, 256, smem, ctx.stream>>>(a);
+      mg_plane_coarse_kernel<<<S.nq, 512, smem, ctx.stream>>>(a);
       ctx.launches++;
     }
   }
 };
 }  // namespace
 
+void MGSolver::stats(Ctx &ctx, int *iters, double *relres, double *mean_iters) {
+  if (plane_local) {
+    std::vector<int> it(nq);
+    std::vector<double> rel(nq);
+    SNAC_CUDA(cudaMemcpyAsync(it.data(), d_iters, nq * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    SNAC_CUDA(cudaMemcpyAsync(rel.data(), norms.raw + 2 * (size_t)nq, nq * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+    last_iters = 0; last_relres = 0.0; last_mean_iters = 0.0;
+    for (int q = 0; q < nq; ++q) {
+      last_iters = std::max(last_iters, it[q]);
+      last_relres = std::max(last_relres, rel[q]);
+      last_mean_iters += it[q];
+    }
+    last_mean_iters /= nq;
+  }
+  if (iters) *iters = last_iters;
+  if (relres) *relres = last_relres;
+  if (mean_iters) *mean_iters = last_mean_iters;
+}
+
+// plane-local path: the stopping test runs on the device, per wavenumber; the host only polls the
+// number of wavenumbers still iterating once per batch of cycles
+static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
+  const int nq = S.nq, ls = S.first_smem_level;
+  const double tol = ctx.prm.hypre_tol;
+  const int maxiter = std::max(ctx.prm.hypre_maxiter, 1);
+  const bool in_alt = ls > 0;
+  SNAC_CUDA(cudaMemsetAsync(S.norms.raw, 0, 3 * (size_t)nq * sizeof(double), ctx.stream));
+  mg_flags_init_kernel<<<1, 256, 0, ctx.stream>>>(S.d_active, S.d_where, S.d_iters, S.d_count, nq);
+  ctx.launches++;
+  int it = 0;
+  for (;;) {
+    const int batch = 3;
+    for (int c = 0; c < batch; ++c, ++it) {
+      if (ls == 0) cy.plane_coarse(true, it == 0);   // the whole cycle in one kernel
+      else cy.plane_down(0, true, it == 0);
+      {
+        ProfScope ps(ctx, PC_MG_COARSE);
+        mg_flags_kernel<<<1, 256, 0, ctx.stream>>>(S.norms.raw, nq, tol * tol, it, maxiter, in_alt ? 1 : 0, S.d_active, S.d_where,
+                                                   S.d_iters, S.d_count);
+        ctx.launches++;
+      }
+      if (ls > 0) {
+        for (int l = 1; l < ls; ++l) cy.plane_down(l, false, false);
+        cy.plane_coarse(false, false);
+        for (int l = ls - 1; l >= 0; --l) cy.plane_up(l);
+      }
+    }
+    SNAC_CUDA(cudaMemcpyAsync(S.h_count, S.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
+    SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (*S.h_count == 0 || it > maxiter) break;
+  }
+  {
+    ProfScope ps(ctx, PC_MG_COARSE);
+    MGLevel &L = *S.levels[0];
+    for (size_t lb = 0; lb < L.boxes.size(); ++lb) {
+      const Grid3 &g = L.boxes[lb].g;
+      dim3 blk(64, 4, 1), grd((g.n[0] + 63) / 64, (g.n[1] + 3) / 4, nq);
+      mg_finalize_kernel<<<grd, blk, 0, ctx.stream>>>(cy.xbuf(0, (int)lb, 0), in_alt ? cy.xbuf(0, (int)lb, 1) : cy.xbuf(0, (int)lb, 0),
+                                                      g.sy, g.sz, g.n[0], g.n[1], S.d_where);
+      ctx.launches++;
+    }
+  }
+}
+
 void MGSolver::solve(Ctx &ctx) {
   Cycle cy{ctx, *this, {fft_dir != 0, fft_dir != 1, fft_dir != 2},
            ctx.prm.mg_npre > 0 ? ctx.prm.mg_npre : 1, ctx.prm.mg_npost > 0 ? ctx.prm.mg_npost : 1,
            ctx.prm.mg_nbottom > 0 ? ctx.prm.mg_nbottom : 20};
+  if (plane_local) {
+    solve_plane_local(ctx, *this, cy);
+    return;
+  }
+  // general multi-box path: the host reads the per-plane residual norms once per cycle
   const int nlev = (int)levels.size();
   const double tol = ctx.prm.hypre_tol;
   const int maxiter = std::max(ctx.prm.hypre_maxiter, 1);
-  const int ls = first_smem_level;
   last_iters = 0;
   last_relres = 0.0;
-  if (!plane_local) cy.exchange(0);
+  cy.exchange(0);
   for (int it = 0;; ++it) {
     const size_t nn = (it == 0 ? 2 : 1) * (size_t)nq * sizeof(double);
     SNAC_CUDA(cudaMemsetAsync(norms.raw, 0, nn, ctx.stream));
     // pre-relaxation on level 0 + residual (+ restriction); its norm drives the stopping test
-    if (plane_local) {
-      if (ls == 0) cy.plane_coarse(true, it == 0);   // the whole cycle in one kernel
-      else cy.plane_down(0, true, it == 0);
-    } else {
-      if (nlev == 1) cy.sweeps(0, cy.nbot, false);
-      else cy.sweeps(0, cy.npre, false);
-      cy.restrict_from(0, true, it == 0);
-    }
+    if (nlev == 1) cy.sweeps(0, cy.nbot, false);
+    else cy.sweeps(0, cy.npre, false);
+    cy.restrict_from(0, true, it == 0);
     SNAC_CUDA(cudaMemcpyAsync(h_norms.data(), norms.raw, nn, cudaMemcpyDeviceToHost, ctx.stream));
     SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
     bool conv = true, any_zero = false;
@@ -977,56 +1350,24 @@ void MGSolver::solve(Ctx &ctx) {
       if (!(rel < tol)) conv = false;
     }
     last_relres = worst;
-    // where the current iterate lives on level 0: the tiled down kernel wrote the other buffer
-    const bool in_alt = plane_local && ls > 0;
     if (it == 0 && any_zero) {   // HYPRE returns x = 0 for b = 0
       MGLevel &L = *levels[0];
       for (size_t lb = 0; lb < L.boxes.size(); ++lb) {
         MGKernelBox B = kbox(*this, L.boxes[lb], (int)lb, cy.coupled);
-        if (in_alt) B.x = cy.xbuf(0, (int)lb, 1);
         dim3 blk = mg_block(L.boxes[lb].g, fft_dir), grd = mg_grid(blk, B.n[0], B.n[1], B.n[2]);
         mg_zero_planes_kernel<<<grd, blk, 0, ctx.stream>>>(B, norms.raw, nq);
-        if (in_alt) {  // keep both buffers consistent
-          B.x = cy.xbuf(0, (int)lb, 0);
-          mg_zero_planes_kernel<<<grd, blk, 0, ctx.stream>>>(B, norms.raw, nq);
-        }
         ctx.launches++;
       }
-      if (!plane_local) {
-        cy.exchange(0);
-        if (worst > 0.0) cy.restrict_from(0, false, false);   // the coarse RHS used the old iterate there
-      }
-      // (plane-local: a zero right-hand side gives a zero residual and a zero correction in that
-      //  plane once x is zero; the stale coarse RHS of this first cycle only perturbs planes that
-      //  are then re-zeroed below)
+      cy.exchange(0);
+      if (worst > 0.0) cy.restrict_from(0, false, false);   // the coarse RHS used the old iterate there
     }
     const bool stop = (it > 0 && conv) || it >= maxiter || (worst == 0.0) || (nlev == 1 && conv);
     if (stop) {
       last_iters = it;
-      if (in_alt) {   // result of the down kernel -> canonical buffer
-        for (size_t lb = 0; lb < levels[0]->boxes.size(); ++lb)
-          SNAC_CUDA(cudaMemcpyAsync(cy.xbuf(0, (int)lb, 0), cy.xbuf(0, (int)lb, 1),
-                                    levels[0]->boxes[lb].g.alloc_elems() * sizeof(double) - 15 * sizeof(double),
-                                    cudaMemcpyDeviceToDevice, ctx.stream));
-      }
+      last_mean_iters = it;
       break;
     }
-    if (plane_local) {
-      if (ls > 0) {
-        for (int l = 1; l < ls; ++l) cy.plane_down(l, false, false);
-        cy.plane_coarse(false, false);
-        for (int l = ls - 1; l >= 0; --l) cy.plane_up(l);
-        if (it == 0 && any_zero) {   // planes with b = 0 stay exactly zero
-          MGLevel &L = *levels[0];
-          for (size_t lb = 0; lb < L.boxes.size(); ++lb) {
-            MGKernelBox B = kbox(*this, L.boxes[lb], (int)lb, cy.coupled);
-            dim3 blk = mg_block(L.boxes[lb].g, fft_dir), grd = mg_grid(blk, B.n[0], B.n[1], B.n[2]);
-            mg_zero_planes_kernel<<<grd, blk, 0, ctx.stream>>>(B, norms.raw, nq);
-            ctx.launches++;
-          }
-        }
-      }
-    } else if (nlev > 1) {
+    if (nlev > 1) {
       cy.descend(1);
       cy.prolong_to(0);
       cy.exchange(0);

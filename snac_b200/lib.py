@@ -76,6 +76,7 @@ EXPORTS = {
     "snac_chkdiv": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "snac_step": (C.c_int, [C.c_void_p, C.c_double]),
     "snac_solver_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "snac_solver_mean_iters": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "snac_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "snac_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "snac_profile_name": (C.c_char_p, [C.c_int]),

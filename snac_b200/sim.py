@@ -182,6 +182,11 @@ class Simulation:
         self._chk(self.lib.snac_solver_stats(self.h, C.byref(it), C.byref(rr)))
         return it.value, rr.value
 
+    def solver_mean_iters(self):
+        v = C.c_double()
+        self._chk(self.lib.snac_solver_mean_iters(self.h, C.byref(v)))
+        return v.value
+
     def launch_count(self):
         return int(self.lib.snac_launch_count(self.h))
 
