@@ -114,6 +114,16 @@ SNAC_API int snac_add_box(snac_handle *h, const snac_box *box);
  * hierarchies (replacing init_matrix_3d, init_matrix_2d, create_solver and setup_solver,
  * src/solver.f90:158-484). */
 SNAC_API int snac_commit(snac_handle *h);
+/* Several processes (one per GPU of a node; params.nproc > 1): every process must add EVERY box of
+ * the run (those it does not own are recorded as descriptions only), commit, publish a blob of
+ * snac_comm_blob_size() bytes, gather the blobs of all processes in process order by its own means
+ * (MPI_Allgather in the reference's setting, src/initmpi.f90:43-248 gathers the same information)
+ * and connect: halos (updthalo, src/bound.f90:587-650) and the wavenumber transposes of the solver
+ * (cf. src/solver.f90:1244-1371) then go over NVLink through CUDA-IPC mapped peer memory. */
+#include <stddef.h>
+SNAC_API size_t snac_comm_blob_size(void);
+SNAC_API int snac_comm_export(snac_handle *h, void *blob);
+SNAC_API int snac_comm_connect(snac_handle *h, const void *blobs, int nblobs);
 SNAC_API int snac_finalize(snac_handle *h);
 SNAC_API const char *snac_last_error(const snac_handle *h);   /* h may be NULL: error of snac_create */
 

@@ -87,12 +87,101 @@ static void build_cen_bc(Ctx &ctx, FaceFill &ff, double *(*get)(Box &, int), int
   ff.upload(ops);
 }
 
+// block-level description used by the batched solver: the boxes of a block are merged so that
+// every 2-D problem lives on one array per block (the transform kernels scatter/gather the pieces)
+struct BlockInfo {
+  int id;
+  int lo_g[3], hi_g[3];
+  int nb[3][2];         // neighbour block or -1
+  int face_rank[3][2];  // a box touching that face
+  std::vector<double> dc[3], df[3];
+};
+
+static std::vector<BlockInfo> assemble_blocks(Ctx &ctx) {
+  std::vector<BlockInfo> blocks;
+  std::vector<int> index_of;   // block id -> index
+  for (int r = 0; r < ctx.prm.nrank; ++r) {
+    if (!ctx.world_set[r]) throw Error("the batched solver needs the description of every box of the run: add box " + std::to_string(r));
+    const snac_box &w = ctx.world[r];
+    if ((int)index_of.size() <= w.block) index_of.resize(w.block + 1, -1);
+    if (index_of[w.block] < 0) {
+      index_of[w.block] = (int)blocks.size();
+      BlockInfo B;
+      B.id = w.block;
+      for (int d = 0; d < 3; ++d) {
+        B.lo_g[d] = w.lo[d]; B.hi_g[d] = w.hi[d];
+        for (int ib = 0; ib < 2; ++ib) { B.nb[d][ib] = -1; B.face_rank[d][ib] = -1; }
+      }
+      blocks.push_back(B);
+    }
+    BlockInfo &B = blocks[index_of[w.block]];
+    for (int d = 0; d < 3; ++d) { B.lo_g[d] = std::min(B.lo_g[d], w.lo[d]); B.hi_g[d] = std::max(B.hi_g[d], w.hi[d]); }
+  }
+  for (BlockInfo &B : blocks)
+    for (int d = 0; d < 3; ++d) {
+      const int N = B.hi_g[d] - B.lo_g[d] + 1;
+      B.dc[d].assign(N + 2, 0.0);
+      B.df[d].assign(N + 2, 0.0);
+    }
+  for (int r = 0; r < ctx.prm.nrank; ++r) {
+    const snac_box &w = ctx.world[r];
+    BlockInfo &B = blocks[index_of[w.block]];
+    for (int d = 0; d < 3; ++d) {
+      const int n = w.hi[d] - w.lo[d] + 1, o = w.lo[d] - B.lo_g[d];
+      for (int q = 0; q <= n + 1; ++q) { B.dc[d][o + q] = ctx.world_dc[d][r][q]; B.df[d][o + q] = ctx.world_df[d][r][q]; }
+      if (w.lo[d] == B.lo_g[d]) B.face_rank[d][0] = r;
+      if (w.hi[d] == B.hi_g[d]) B.face_rank[d][1] = r;
+    }
+  }
+  for (BlockInfo &B : blocks)
+    for (int d = 0; d < 3; ++d)
+      for (int ib = 0; ib < 2; ++ib) {
+        const int fr = B.face_rank[d][ib];
+        const int nbr = ctx.world[fr].nb[d][ib];
+        B.nb[d][ib] = nbr < 0 ? -1 : index_of[ctx.world[nbr].block];
+      }
+  return blocks;
+}
+
+static void q_range(const Ctx &ctx, int nq, int proc, int &q0, int &q1) {
+  const int chunk = (nq + ctx.comm.nproc - 1) / ctx.comm.nproc;
+  q0 = std::min(nq, proc * chunk);
+  q1 = std::min(nq, q0 + chunk);
+}
+
+static void alloc_field(Ctx &ctx, Field3 &f, const Grid3 &g, int id, int key) {
+  if (ctx.comm.nproc > 1) f.adopt(ctx.comm.alloc(g.alloc_elems(), id, key));
+  else f.alloc(g);
+}
+
+static void finish_setup(Ctx &ctx);
+
 static void commit(Ctx &ctx) {
   if (ctx.committed) throw Error("snac_commit called twice");
   if (ctx.boxes.empty()) throw Error("snac_commit: no boxes were added");
   const int fa = ctx.prm.fft_axis - 1;
+  const bool batched = ctx.prm.fft_axis > 0;
+  const int nl = (int)ctx.boxes.size();
+  std::vector<BlockInfo> blocks;
+  if (batched) blocks = assemble_blocks(ctx);
+  ctx.nq = batched ? ctx.boxes[0]->g.n[fa] : 1;
+  q_range(ctx, ctx.nq, ctx.comm.me, ctx.q0, ctx.q1);
+  if (batched && ctx.q1 <= ctx.q0) throw Error("more processes than wavenumbers: nothing to solve on this process");
+  if (ctx.comm.nproc > 1) {
+    if (!batched) throw Error("a 3-D solve (fft_axis = 0) distributed over several processes is not available in this build");
+    size_t bytes = 0;
+    for (auto &bp : ctx.boxes) bytes += (size_t)(8 + ctx.prm.nscal) * (bp->g.alloc_elems() * sizeof(double) + 256);
+    for (BlockInfo &B : blocks) {
+      int pd[2], q = 0;
+      for (int d = 0; d < 3; ++d) if (d != fa) pd[q++] = d;
+      Grid3 sg = Grid3::make(B.hi_g[pd[0]] - B.lo_g[pd[0]] + 1, B.hi_g[pd[1]] - B.lo_g[pd[1]] + 1, std::max(ctx.q1 - ctx.q0, 1));
+      bytes += 2 * (sg.alloc_elems() * sizeof(double) + 256);
+    }
+    ctx.comm.init(ctx.prm.nproc, ctx.prm.myproc, bytes);
+  }
   for (auto &bp : ctx.boxes) {
     Box &b = *bp;
+    const int r = b.info.rank;
     for (int d = 0; d < 3; ++d) {
       const int n = b.g.n[d];
       std::vector<double> rc(n + 2), rf(n + 2), wq(n + 2), gq(n + 2);
@@ -106,17 +195,119 @@ static void commit(Ctx &ctx) {
       b.rdc[d].upload(rc); b.rdf[d].upload(rf);
       b.wq[d].upload(wq); b.gq[d].upload(gq);
     }
-    for (int q = 0; q < 2; ++q) { b.u[q].alloc(b.g); b.v[q].alloc(b.g); b.w[q].alloc(b.g); }
-    b.p.alloc(b.g); b.rhs.alloc(b.g);
-    b.pp_is_po = (ctx.prm.fft_axis == 0);
+    for (int q = 0; q < 2; ++q) {
+      alloc_field(ctx, b.u[q], b.g, r, AK_U0 + q);
+      alloc_field(ctx, b.v[q], b.g, r, AK_V0 + q);
+      alloc_field(ctx, b.w[q], b.g, r, AK_W0 + q);
+    }
+    alloc_field(ctx, b.p, b.g, r, AK_P);
+    b.rhs.alloc(b.g);
+    b.pp_is_po = !batched;
     if (b.pp_is_po) b.po.alloc(b.g);
-    else { b.pp.alloc(b.g); b.stage.alloc(b.g); }
+    else { alloc_field(ctx, b.pp, b.g, r, AK_PP); b.stage.alloc(b.g); }
     b.du.alloc(b.g); b.dv.alloc(b.g); b.dw.alloc(b.g);
-    for (int s = 0; s < ctx.prm.nscal; ++s) { b.s[s].alloc(b.g); b.ds[s].alloc(b.g); }
+    for (int s = 0; s < ctx.prm.nscal; ++s) { alloc_field(ctx, b.s[s], b.g, r, AK_S0 + s); b.ds[s].alloc(b.g); }
     compute_bc_rhs(ctx, b);
   }
+  // transforms (fftini for the pressure, src/main.f90:735)
+  if (batched) {
+    Box &b0 = *ctx.boxes[0];
+    const char bc[2] = {b0.info.cbcpre[fa][0], b0.info.cbcpre[fa][1]};
+    for (int r = 0; r < ctx.prm.nrank; ++r) {
+      const snac_box &w = ctx.world[r];
+      if (w.hi[fa] - w.lo[fa] + 1 != b0.g.n[fa] || w.cbcpre[fa][0] != bc[0] || w.cbcpre[fa][1] != bc[1])
+        throw Error("all boxes must have the same size and boundary conditions along the transform axis (src/sanity.f90:66-100)");
+    }
+    r2r_plan_init(ctx.plan_p, fa, b0.g.n[fa], bc, true);
+  }
+  {  // the pressure problem as the solver sees it
+    MGSolver &S = ctx.psolver;
+    std::vector<SBox> sb;
+    if (batched) {
+      // canonical layout: coupled directions first, the transform direction (batch) last; one solver
+      // box per block; this process solves the wavenumbers q0..q1-1
+      int q = 0;
+      for (int d = 0; d < 3; ++d) if (d != fa) S.perm[q++] = d;
+      S.perm[2] = fa;
+      sb.resize(blocks.size());
+      ctx.block_index.assign(1, -1);
+      for (size_t ib_ = 0; ib_ < blocks.size(); ++ib_) {
+        BlockInfo &B = blocks[ib_];
+        if ((int)ctx.block_index.size() <= B.id) ctx.block_index.resize(B.id + 1, -1);
+        ctx.block_index[B.id] = (int)ib_;
+        SBox &s = sb[ib_];
+        const snac_box &w0 = ctx.world[B.face_rank[fa][0]];
+        for (int sd = 0; sd < 3; ++sd) {
+          const int d = S.perm[sd];
+          s.n[sd] = sd == 2 ? (ctx.q1 - ctx.q0) : (B.hi_g[d] - B.lo_g[d] + 1);
+          s.d1[sd] = B.dc[d];
+          s.d2[sd] = B.df[d];
+          for (int ib = 0; ib < 2; ++ib) {
+            const snac_box &wf = ctx.world[B.face_rank[d][ib]];
+            s.nb[sd][ib] = B.nb[d][ib];
+            s.phys[sd][ib] = wf.is_bound[d][ib] && ctx.prm.periods[d] == 0;
+            s.sgn[sd][ib] = 0.0;
+            if (s.phys[sd][ib] && sd != 2) {   // src/solver.f90:71-94 (centred unknowns)
+              const char c = wf.cbcpre[d][ib];
+              if (c == 'N') s.sgn[sd][ib] = 1.0;
+              else if (c == 'D') s.sgn[sd][ib] = -1.0;
+              else throw Error("pressure boundary condition on a physical face must be 'D' or 'N'");
+            }
+          }
+        }
+        // eigenvalues / dl^2 of this process' wavenumbers (src/fft.f90:151-189, src/solver.f90:1124-1138)
+        const char bc[2] = {w0.cbcpre[fa][0], w0.cbcpre[fa][1]};
+        std::vector<double> l = r2r_eigenvalues(ctx.nq, bc, true);
+        const double dl = w0.dl[fa][0];
+        s.lam.assign((size_t)(ctx.q1 - ctx.q0) + 2, 0.0);
+        for (int k = ctx.q0; k < ctx.q1; ++k) s.lam[k - ctx.q0 + 1] = l[k] / (dl * dl);
+        if (ctx.comm.nproc > 1) {   // slabs live in the arena: peers write the right-hand side and read the solution
+          Grid3 sg = Grid3::make(s.n[0], s.n[1], std::max(s.n[2], 1));
+          s.x = ctx.comm.alloc(sg.alloc_elems(), B.id, AK_SLAB_X) + 15;
+          s.b = ctx.comm.alloc(sg.alloc_elems(), B.id, AK_SLAB_B) + 15;
+        }
+      }
+      ctx.blocks_lo.clear();
+      for (BlockInfo &B : blocks) ctx.blocks_lo.push_back({B.lo_g[0], B.lo_g[1], B.lo_g[2]});
+    } else {
+      sb.resize(nl);
+      for (int lb = 0; lb < nl; ++lb) {
+        Box &b = *ctx.boxes[lb];
+        SBox &s = sb[lb];
+        for (int d = 0; d < 3; ++d) {
+          s.n[d] = b.g.n[d];
+          s.d1[d] = b.h_dc[d];
+          s.d2[d] = b.h_df[d];
+          for (int ib = 0; ib < 2; ++ib) {
+            s.nb[d][ib] = b.info.nb[d][ib];
+            s.phys[d][ib] = b.info.is_bound[d][ib] && ctx.prm.periods[d] == 0;
+            s.sgn[d][ib] = 0.0;
+            if (s.phys[d][ib]) {
+              const char c = b.info.cbcpre[d][ib];
+              if (c == 'N') s.sgn[d][ib] = 1.0;
+              else if (c == 'D') s.sgn[d][ib] = -1.0;
+              else throw Error("pressure boundary condition on a physical face must be 'D' or 'N'");
+            }
+          }
+        }
+        s.x = b.po.p;
+        s.b = b.rhs.p;
+      }
+    }
+    S.setup(ctx, std::move(sb), batched);
+  }
+  ctx.red.alloc(8);
+  SNAC_CUDA(cudaMallocHost(&ctx.h_red, 4 * MAXPROC * sizeof(double)));
+  SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+  ctx.committed = true;
+  if (ctx.comm.nproc == 1) finish_setup(ctx);
+}
+
+// halo tables, boundary-condition tables and transform routing: needs the peers' arenas when
+// several processes take part (called from snac_comm_connect in that case)
+static void finish_setup(Ctx &ctx) {
   const int nl = (int)ctx.boxes.size();
-  // halo exchanges
+  const int fa = ctx.prm.fft_axis - 1;
   for (int par = 0; par < 2; ++par) {
     std::vector<ExField> ef;
     for (int f = 0; f < 3; ++f)
@@ -124,7 +315,8 @@ static void commit(Ctx &ctx) {
         Box &b = *ctx.boxes[lb];
         ef.push_back(ExField{lb, f == 0 ? b.u[par].p : (f == 1 ? b.v[par].p : b.w[par].p), b.g});
       }
-    ctx.ex_uvw[par].build(ctx, ef);
+    const std::vector<int> keys = {AK_U0 + par, AK_V0 + par, AK_W0 + par};
+    ctx.ex_uvw[par].build(ctx, ef, nullptr, &keys);
     build_vel_bc(ctx, par, false, ctx.bc_uvw[par][0]);
     build_vel_bc(ctx, par, true, ctx.bc_uvw[par][1]);
   }
@@ -135,8 +327,9 @@ static void commit(Ctx &ctx) {
       ep.push_back(ExField{lb, b.p.p, b.g});
       epp.push_back(ExField{lb, b.pp_ptr(), b.g});
     }
-    ctx.ex_p.build(ctx, ep);
-    ctx.ex_pp.build(ctx, epp);
+    const std::vector<int> kp = {AK_P}, kpp = {AK_PP};
+    ctx.ex_p.build(ctx, ep, nullptr, &kp);
+    ctx.ex_pp.build(ctx, epp, nullptr, &kpp);
     auto cbc = [](Box &b, int, int d, int ib) -> char { return b.info.cbcpre[d][ib]; };
     auto bc = [](Box &b, int, int d, int ib) -> double { return b.info.bcpre[d][ib]; };
     build_cen_bc(ctx, ctx.bc_p, [](Box &b, int) { return b.p.p; }, 0, cbc, bc);
@@ -145,66 +338,41 @@ static void commit(Ctx &ctx) {
   for (int s = 0; s < ctx.prm.nscal; ++s) {
     std::vector<ExField> es;
     for (int lb = 0; lb < nl; ++lb) es.push_back(ExField{lb, ctx.boxes[lb]->s[s].p, ctx.boxes[lb]->g});
-    ctx.ex_s[s].build(ctx, es);
+    const std::vector<int> ks = {AK_S0 + s};
+    ctx.ex_s[s].build(ctx, es, nullptr, &ks);
     auto cbc = [](Box &b, int s_, int d, int ib) -> char { return b.info.cbcscal[s_][d][ib]; };
     auto bc = [](Box &b, int s_, int d, int ib) -> double { return b.info.bcscal[s_][d][ib]; };
     build_cen_bc(ctx, ctx.bc_s[s], [](Box &b, int s_) { return b.s[s_].p; }, s, cbc, bc);
   }
-  // transforms (fftini for the pressure, src/main.f90:735) and the Poisson solver
+  // transform routing: where each local box's pencils go to / come from, per owning process
   if (ctx.prm.fft_axis > 0) {
-    Box &b0 = *ctx.boxes[0];
-    const char bc[2] = {b0.info.cbcpre[fa][0], b0.info.cbcpre[fa][1]};
-    for (auto &bp : ctx.boxes)
-      if (bp->g.n[fa] != b0.g.n[fa] || bp->info.cbcpre[fa][0] != bc[0] || bp->info.cbcpre[fa][1] != bc[1])
-        throw Error("all boxes must have the same size and boundary conditions along the transform axis (src/sanity.f90:66-100)");
-    r2r_plan_init(ctx.plan_p, fa, b0.g.n[fa], bc, true);
-  }
-  {  // the pressure problem as the solver sees it: canonical (permuted) layout when batched
-    const bool batched = ctx.prm.fft_axis > 0;
     MGSolver &S = ctx.psolver;
-    if (batched) {
-      int q = 0;
-      for (int d = 0; d < 3; ++d) if (d != fa) S.perm[q++] = d;
-      S.perm[2] = fa;
-    }
-    std::vector<SBox> sb(nl);
+    ctx.route.assign(nl, FFTRoute());
     for (int lb = 0; lb < nl; ++lb) {
       Box &b = *ctx.boxes[lb];
-      SBox &s = sb[lb];
-      for (int sd = 0; sd < 3; ++sd) {
-        const int d = S.perm[sd];
-        s.n[sd] = b.g.n[d];
-        s.d1[sd] = b.h_dc[d];
-        s.d2[sd] = b.h_df[d];
-        for (int ib = 0; ib < 2; ++ib) {
-          s.nb[sd][ib] = b.info.nb[d][ib];
-          s.phys[sd][ib] = b.info.is_bound[d][ib] && ctx.prm.periods[d] == 0;
-          s.sgn[sd][ib] = 0.0;
-          if (s.phys[sd][ib] && !(batched && sd == 2)) {   // src/solver.f90:71-94 (centred unknowns)
-            const char c = b.info.cbcpre[d][ib];
-            if (c == 'N') s.sgn[sd][ib] = 1.0;
-            else if (c == 'D') s.sgn[sd][ib] = -1.0;
-            else throw Error("pressure boundary condition on a physical face must be 'D' or 'N'");
-          }
-        }
-      }
-      if (batched) {  // eigenvalues / dl^2 (src/fft.f90:151-189, src/solver.f90:1124-1138)
-        const char bc[2] = {b.info.cbcpre[fa][0], b.info.cbcpre[fa][1]};
-        std::vector<double> l = r2r_eigenvalues(b.g.n[fa], bc, true);
-        const double dl = b.info.dl[fa][0];
-        s.lam.assign(l.size() + 2, 0.0);
-        for (size_t k = 0; k < l.size(); ++k) s.lam[k + 1] = l[k] / (dl * dl);
-      } else {
-        s.x = b.po.p;
-        s.b = b.rhs.p;
+      const int bi = ctx.block_index[b.info.block];
+      const Grid3 &sg = S.grid0(bi);
+      FFTRoute &R = ctx.route[lb];
+      for (int sd = 0; sd < 3; ++sd) R.st[S.perm[sd]] = sg.st(sd);
+      // offset of this box's first cell inside the block's array (coupled directions only)
+      long off = 1 + sg.sy + sg.sz;
+      for (int sd = 0; sd < 2; ++sd) off += (long)(b.info.lo[S.perm[sd]] - ctx.blocks_lo[bi][S.perm[sd]]) * sg.st(sd);
+      R.chunk = (ctx.nq + ctx.comm.nproc - 1) / ctx.comm.nproc;
+      R.nsplit = ctx.comm.nproc;
+      for (int p = 0; p < ctx.comm.nproc; ++p) {
+        int q0, q1;
+        q_range(ctx, ctx.nq, p, q0, q1);
+        double *xb, *bb;
+        if (p == ctx.comm.me) { xb = S.xcur(bi); bb = S.bcur(bi); }
+        else { xb = ctx.comm.remote(p, b.info.block, AK_SLAB_X) + 15; bb = ctx.comm.remote(p, b.info.block, AK_SLAB_B) + 15; }
+        // the wavenumber index is absolute in the kernels: shift by the slab origin
+        R.x[p] = xb + off - (long)q0 * sg.st(2);
+        R.b[p] = bb + off - (long)q0 * sg.st(2);
       }
     }
-    S.setup(ctx, std::move(sb), batched);
+    (void)fa;
   }
-  ctx.red.alloc(8);
-  SNAC_CUDA(cudaMallocHost(&ctx.h_red, 8 * sizeof(double)));
-  SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
-  ctx.committed = true;
+  ctx.ready = true;
 }
 
 static Field3 *field_of(Ctx &ctx, Box &b, int field, bool &ghost_alias_pp) {
@@ -226,13 +394,6 @@ static Field3 *field_of(Ctx &ctx, Box &b, int field, bool &ghost_alias_pp) {
   throw Error("unknown field id " + std::to_string(field));
 }
 
-// strides of the physical directions in the solver's canonical array of local box lb
-static void solver_strides(Ctx &ctx, int lb, long st[3]) {
-  const MGSolver &S = ctx.psolver;
-  const Grid3 &g = S.grid0(lb);
-  for (int sd = 0; sd < 3; ++sd) st[S.perm[sd]] = g.st(sd);
-}
-
 __global__ void permute_copy_kernel(double *dst, long d0, long d1, long d2, const double *src, long s0, long s1, long s2,
                                     int n0, int n1, int n2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
@@ -243,25 +404,25 @@ static void transfer(Ctx &ctx, int rank, int field, double *host, bool up) {
   Box &b = ctx.box_of_rank(rank);
   const int lb = ctx.local_of_rank[rank];
   const bool batched = ctx.prm.fft_axis > 0;
-  // spectral arrays live in the solver's canonical layout: go through a staging array
+  // spectral arrays live in the solver's canonical per-block layout: go through a staging array
   const bool spectral = batched && (field == SNAC_FIELD_PO || field == SNAC_FIELD_RHS_HAT);
+  if (spectral && ctx.comm.nproc > 1) throw Error("spectral fields are distributed over the processes: transfer is single-process only");
   Field3 *f;
   bool dummy;
   if (spectral) f = &b.stage;
   else if (field == SNAC_FIELD_RHS_HAT) f = &b.rhs;
   else f = field_of(ctx, b, field, dummy);
-  long sst[3] = {0, 0, 0};
-  double *sp = nullptr;
-  long pint = 1 + b.g.sy + b.g.sz, sint = 0;
+  const long pint = 1 + b.g.sy + b.g.sz;
   dim3 blk(32, 8, 1), grd((b.g.n[0] + 31) / 32, (b.g.n[1] + 7) / 8, b.g.n[2]);
+  double *sp = nullptr;
+  const long *sst = nullptr;
   if (spectral) {
-    solver_strides(ctx, lb, sst);
-    const Grid3 &sg = ctx.psolver.grid0(lb);
-    sint = 1 + sg.sy + sg.sz;
-    sp = field == SNAC_FIELD_PO ? ctx.psolver.xcur(lb) : ctx.psolver.bcur(lb);
+    const FFTRoute &R = ctx.route[lb];
+    sst = R.st;
+    sp = field == SNAC_FIELD_PO ? R.x[0] : R.b[0];   // first interior element of this box inside its block's array
     if (!up) {
       SNAC_CUDA(cudaMemsetAsync(b.stage.buf.raw, 0, b.stage.buf.elems * sizeof(double), ctx.stream));
-      permute_copy_kernel<<<grd, blk, 0, ctx.stream>>>(b.stage.p + pint, 1, b.g.sy, b.g.sz, sp + sint, sst[0], sst[1], sst[2],
+      permute_copy_kernel<<<grd, blk, 0, ctx.stream>>>(b.stage.p + pint, 1, b.g.sy, b.g.sz, sp, sst[0], sst[1], sst[2],
                                                        b.g.n[0], b.g.n[1], b.g.n[2]);
     }
   }
@@ -276,7 +437,7 @@ static void transfer(Ctx &ctx, int rank, int field, double *host, bool up) {
   prm.kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
   SNAC_CUDA(cudaMemcpy3DAsync(&prm, ctx.stream));
   if (spectral && up)
-    permute_copy_kernel<<<grd, blk, 0, ctx.stream>>>(sp + sint, sst[0], sst[1], sst[2], b.stage.p + pint, 1, b.g.sy, b.g.sz,
+    permute_copy_kernel<<<grd, blk, 0, ctx.stream>>>(sp, sst[0], sst[1], sst[2], b.stage.p + pint, 1, b.g.sy, b.g.sz,
                                                      b.g.n[0], b.g.n[1], b.g.n[2]);
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
 }
@@ -304,30 +465,68 @@ static void do_boundp(Ctx &ctx, int field) {
 }
 static void do_fft(Ctx &ctx, int dir) {
   if (ctx.prm.fft_axis == 0) throw Error("fft: the handle was created with fft_axis = 0");
+  if (!ctx.ready) throw Error("snac_comm_connect has not been called");
   ProfScope ps(ctx, dir > 0 ? PC_FFT_FWD : PC_FFT_BWD);
-  const MGSolver &S = ctx.psolver;
   for (int lb = 0; lb < (int)ctx.boxes.size(); ++lb) {
     Box &b = *ctx.boxes[lb];
-    long pst[3] = {1, b.g.sy, b.g.sz}, sst[3];
-    solver_strides(ctx, lb, sst);
-    const Grid3 &sg = S.grid0(lb);
-    const long pint = 1 + b.g.sy + b.g.sz, sint = 1 + sg.sy + sg.sz;   // first interior element
-    if (dir > 0) r2r_execute(ctx, ctx.plan_p, +1, b.g.n, b.rhs.p + pint, pst, S.bcur(lb) + sint, sst, 1.0);
-    else r2r_execute(ctx, ctx.plan_p, -1, b.g.n, S.xcur(lb) + sint, sst, b.pp.p + pint, pst, ctx.plan_p.normfft);
+    const FFTRoute &R = ctx.route[lb];
+    const long pst[3] = {1, b.g.sy, b.g.sz};
+    const long pint = 1 + b.g.sy + b.g.sz;   // first interior element
+    if (dir > 0) {        // physical right-hand side -> the owners' slabs
+      const double *in[1] = {b.rhs.p + pint};
+      r2r_execute(ctx, ctx.plan_p, +1, b.g.n, in, 1, pst, R.b, R.nsplit, R.st, R.chunk, 1.0);
+    } else {              // the owners' solution slabs -> physical pp, times normfft (src/main.f90:1017-1020)
+      double *out[1] = {b.pp.p + pint};
+      r2r_execute(ctx, ctx.plan_p, -1, b.g.n, R.x, R.nsplit, R.st, out, 1, pst, R.chunk, ctx.plan_p.normfft);
+    }
   }
+  // forward: every process must have received all pieces of its slabs before solving
+  if (dir > 0) ctx.comm.handshake(ctx, CH_FFT, ~0u);
 }
-static void do_solve(Ctx &ctx) { ctx.psolver.solve(ctx); }
+static void do_solve(Ctx &ctx) {
+  ctx.psolver.solve(ctx);
+  // batched: the peers read this process' solution slab in the backward transform
+  if (ctx.prm.fft_axis > 0) ctx.comm.handshake(ctx, CH_SOLVED, ~0u);
+}
 
+__global__ void publish_kernel(const double *vals, double *const *slots, int n, int nproc) {
+  const int p = threadIdx.x;
+  if (p < nproc) for (int i = 0; i < n; ++i) slots[p][i] = vals[i];
+}
+
+// local reductions, then the MPI_ALLREDUCEs of chkdt/chkdiv (src/chkdt.f90:48, src/chkdiv.f90:42-43):
+// every process writes its three partial results into every peer's arena and reduces on the host
 static void do_chk(Ctx &ctx, bool want_dt, double *out3) {
   SNAC_CUDA(cudaMemsetAsync(ctx.red.raw, 0, 8 * sizeof(double), ctx.stream));
   {
     ProfScope ps(ctx, PC_CHK);
     for (auto &b : ctx.boxes) launch_chk(ctx, *b, ctx.red.raw);
   }
-  SNAC_CUDA(cudaMemcpyAsync(ctx.h_red, ctx.red.raw, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
   (void)want_dt;
-  for (int q = 0; q < 3; ++q) out3[q] = ctx.h_red[q];
+  const int np = ctx.comm.nproc;
+  if (np == 1) {
+    SNAC_CUDA(cudaMemcpyAsync(ctx.h_red, ctx.red.raw, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+    for (int q = 0; q < 3; ++q) out3[q] = ctx.h_red[q];
+    return;
+  }
+  if (!ctx.ready) throw Error("snac_comm_connect has not been called");
+  // slot of process `me` in the reduction table of every arena (double-buffered by parity of the sequence)
+  const size_t base = PeerComm::FLAGS_BYTES + (size_t)((ctx.comm.seq[CH_REDUCE] + 1) & 1) * MAXPROC * 4 * sizeof(double);
+  std::vector<double *> slots(np);
+  for (int p = 0; p < np; ++p) slots[p] = reinterpret_cast<double *>(ctx.comm.peer[p] + base) + 4 * ctx.comm.me;
+  SNAC_CUDA(cudaMemcpyAsync(ctx.d_slots, slots.data(), np * sizeof(double *), cudaMemcpyHostToDevice, ctx.stream));
+  publish_kernel<<<1, 32, 0, ctx.stream>>>(ctx.red.raw, ctx.d_slots, 3, np);
+  ctx.launches++;
+  ctx.comm.handshake(ctx, CH_REDUCE, ~0u);
+  SNAC_CUDA(cudaMemcpyAsync(ctx.h_red, ctx.comm.arena + base, 4 * MAXPROC * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+  out3[0] = 0.0; out3[1] = 0.0; out3[2] = 0.0;
+  for (int p = 0; p < np; ++p) {
+    out3[0] = std::max(out3[0], ctx.h_red[4 * p + 0]);
+    out3[1] += ctx.h_red[4 * p + 1];
+    out3[2] = std::max(out3[2], ctx.h_red[4 * p + 2]);
+  }
 }
 
 static void substep(Ctx &ctx, int irk, double dt) {
@@ -393,6 +592,13 @@ int snac_create(const snac_params *params, snac_handle **out) {
     if (params->rank_owner) ctx.owner.assign(params->rank_owner, params->rank_owner + params->nrank);
     ctx.prm.rank_owner = nullptr;
     ctx.local_of_rank.assign(params->nrank, -1);
+    ctx.world.assign(params->nrank, snac_box());
+    ctx.world_set.assign(params->nrank, 0);
+    for (int d = 0; d < 3; ++d) { ctx.world_dc[d].assign(params->nrank, {}); ctx.world_df[d].assign(params->nrank, {}); }
+    ctx.comm.nproc = std::max(params->nproc, 1);
+    ctx.comm.me = params->myproc;
+    if (ctx.comm.nproc > MAXPROC) throw Error("snac_create: too many processes");
+    SNAC_CUDA(cudaMalloc(&ctx.d_slots, MAXPROC * sizeof(double *)));
     SNAC_CUDA(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
     SNAC_CUDA(cudaEventCreate(&ctx.prof_ev[0]));
     SNAC_CUDA(cudaEventCreate(&ctx.prof_ev[1]));
@@ -413,23 +619,32 @@ int snac_add_box(snac_handle *h, const snac_box *box) {
     Ctx &ctx = h->ctx;
     if (ctx.committed) throw Error("snac_add_box after snac_commit");
     if (!box || box->rank < 0 || box->rank >= ctx.prm.nrank) throw Error("snac_add_box: bad box id");
-    if (ctx.owner[box->rank] != ctx.prm.myproc) throw Error("snac_add_box: box is owned by another process");
-    if (ctx.local_of_rank[box->rank] >= 0) throw Error("snac_add_box: box added twice");
-    std::unique_ptr<Box> b(new Box);
-    b->info = *box;
+    if (ctx.world_set[box->rank]) throw Error("snac_add_box: box added twice");
     int n[3];
     for (int d = 0; d < 3; ++d) {
       n[d] = box->hi[d] - box->lo[d] + 1;
       if (n[d] < 1) throw Error("snac_add_box: empty box");
     }
-    b->g = Grid3::make(n[0], n[1], n[2]);
     const double *dc[3] = {box->dxc, box->dyc, box->dzc}, *df[3] = {box->dxf, box->dyf, box->dzf};
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < 3; ++d)
       if (!dc[d] || !df[d]) throw Error("snac_add_box: missing grid arrays");
-      b->h_dc[d].assign(dc[d], dc[d] + n[d] + 2);
-      b->h_df[d].assign(df[d], df[d] + n[d] + 2);
+    // every box of the run is recorded (several processes: neighbours and whole blocks must be known)
+    ctx.world[box->rank] = *box;
+    ctx.world[box->rank].dxc = ctx.world[box->rank].dxf = ctx.world[box->rank].dyc = nullptr;
+    ctx.world[box->rank].dyf = ctx.world[box->rank].dzc = ctx.world[box->rank].dzf = nullptr;
+    for (int d = 0; d < 3; ++d) {
+      ctx.world_dc[d][box->rank].assign(dc[d], dc[d] + n[d] + 2);
+      ctx.world_df[d][box->rank].assign(df[d], df[d] + n[d] + 2);
     }
-    b->info.dxc = b->info.dxf = b->info.dyc = b->info.dyf = b->info.dzc = b->info.dzf = nullptr;
+    ctx.world_set[box->rank] = 1;
+    if (ctx.owner[box->rank] != ctx.prm.myproc) return 0;   // owned by another process: description only
+    std::unique_ptr<Box> b(new Box);
+    b->info = ctx.world[box->rank];
+    b->g = Grid3::make(n[0], n[1], n[2]);
+    for (int d = 0; d < 3; ++d) {
+      b->h_dc[d] = ctx.world_dc[d][box->rank];
+      b->h_df[d] = ctx.world_df[d][box->rank];
+    }
     ctx.local_of_rank[box->rank] = (int)ctx.boxes.size();
     ctx.boxes.push_back(std::move(b));
   })
@@ -437,10 +652,31 @@ int snac_add_box(snac_handle *h, const snac_box *box) {
 
 int snac_commit(snac_handle *h) { SNAC_TRY(h, commit(h->ctx)) }
 
+size_t snac_comm_blob_size(void) { return sizeof(CommBlob); }
+int snac_comm_export(snac_handle *h, void *blob) {
+  SNAC_TRY(h, {
+    if (!h->ctx.committed) throw Error("snac_comm_export before snac_commit");
+    if (h->ctx.comm.nproc == 1) { std::memset(blob, 0, sizeof(CommBlob)); return 0; }
+    h->ctx.comm.export_blob(*static_cast<CommBlob *>(blob));
+  })
+}
+int snac_comm_connect(snac_handle *h, const void *blobs, int nblobs) {
+  SNAC_TRY(h, {
+    Ctx &ctx = h->ctx;
+    if (!ctx.committed) throw Error("snac_comm_connect before snac_commit");
+    if (ctx.comm.nproc == 1) return 0;
+    if (ctx.ready) throw Error("snac_comm_connect called twice");
+    ctx.comm.connect(static_cast<const CommBlob *>(blobs), nblobs);
+    finish_setup(ctx);
+  })
+}
+
 int snac_finalize(snac_handle *h) {
   if (!h) return -2;
   cudaStreamSynchronize(h->ctx.stream);
   if (h->ctx.h_red) cudaFreeHost(h->ctx.h_red);
+  if (h->ctx.d_slots) cudaFree(h->ctx.d_slots);
+  h->ctx.comm.release();
   cudaStream_t s = h->ctx.stream;
   delete h;
   if (s) cudaStreamDestroy(s);

@@ -66,37 +66,56 @@ void launch_face_ops(Ctx &ctx, const DevOps<FaceOp> &ops) {
   ctx.launches++;
 }
 
-void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::vector<NbTable> *nbs) {
-  // `fields` holds, for each exchanged array, one entry per local box, grouped:
-  // fields[f*nlocal + lb].  Ghost plane of box lb on side ib comes from the neighbour's first/last
-  // interior plane (src/bound.f90:602-607).
-  const int nl = (int)ctx.boxes.size();
+void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::vector<NbTable> *nbs, const std::vector<int> *keys,
+                     bool ids_local) {
+  // `fields` holds, for each exchanged array, one entry per local box, grouped: fields[f*nl + lb].
+  // Neighbour on this GPU: the ghost plane of box lb on side ib is pulled from the neighbour's
+  // first/last interior plane (src/bound.f90:602-607).  Neighbour owned by another process: this
+  // box's first/last interior plane is pushed into the neighbour's ghost plane in the peer's arena.
+  const int nl = nbs ? (int)nbs->size() : (int)ctx.boxes.size();
   if (fields.size() % nl) throw Error("Exchange::build: field list is not a multiple of the box count");
   std::vector<CopyOp> ops[3];
+  for (int d = 0; d < 3; ++d) mask[d] = 0;
+  key0 = (keys && ctx.comm.nproc > 1) ? (*keys)[0] : -1;   // only exchanges of published arrays synchronise with peers
   for (size_t f = 0; f < fields.size() / nl; ++f) {
     for (int lb = 0; lb < nl; ++lb) {
       const ExField &me = fields[f * nl + lb];
-      const snac_box &info = ctx.boxes[lb]->info;
       for (int d = 0; d < 3; ++d) {
         const int a = (d + 1) % 3, b = (d + 2) % 3;
         const int da = std::min(a, b), db = std::max(a, b);  // keep x (or y) fastest in the plane
         for (int ib = 0; ib < 2; ++ib) {
-          const int nbr = nbs ? (*nbs)[lb].nb[d][ib] : info.nb[d][ib];
+          const int nbr = nbs ? (*nbs)[lb].nb[d][ib] : ctx.boxes[lb]->info.nb[d][ib];
           if (nbr < 0) continue;
-          const int ln = ctx.local_of_rank[nbr];
-          if (ln < 0) throw Error("halo exchange with a box owned by another process is not available in this build");
-          const ExField &src = fields[f * nl + ln];
-          if (src.g.n[da] != me.g.n[da] || src.g.n[db] != me.g.n[db])
-            throw Error("halo exchange: neighbouring boxes are not face-congruent");
+          const int ln = ids_local ? nbr : ctx.local_of_rank[nbr];
           CopyOp op;
           op.na = me.g.n[da] + 2;
           op.nb = me.g.n[db] + 2;
-          op.ssa = src.g.st(da); op.ssb = src.g.st(db);
-          op.dsa = me.g.st(da);  op.dsb = me.g.st(db);
-          const long sidx = (ib == 0) ? src.g.n[d] : 1;          // neighbour's hi / lo interior plane
-          const long didx = (ib == 0) ? 0 : me.g.n[d] + 1;        // my lo / hi ghost plane
-          op.src = src.p + sidx * src.g.st(d);
-          op.dst = me.p + didx * me.g.st(d);
+          if (ln >= 0) {
+            const ExField &src = fields[f * nl + ln];
+            if (src.g.n[da] != me.g.n[da] || src.g.n[db] != me.g.n[db])
+              throw Error("halo exchange: neighbouring boxes are not face-congruent");
+            op.ssa = src.g.st(da); op.ssb = src.g.st(db);
+            op.dsa = me.g.st(da);  op.dsb = me.g.st(db);
+            const long sidx = (ib == 0) ? src.g.n[d] : 1;          // neighbour's hi / lo interior plane
+            const long didx = (ib == 0) ? 0 : me.g.n[d] + 1;        // my lo / hi ghost plane
+            op.src = src.p + sidx * src.g.st(d);
+            op.dst = me.p + didx * me.g.st(d);
+          } else {
+            if (!keys || ctx.comm.nproc == 1) throw Error("halo exchange with a box owned by another process needs snac_comm_connect");
+            const int proc = ctx.owner[nbr];
+            const snac_box &w = ctx.world[nbr];
+            const Grid3 rg = Grid3::make(w.hi[0] - w.lo[0] + 1, w.hi[1] - w.lo[1] + 1, w.hi[2] - w.lo[2] + 1);
+            if (rg.n[da] != me.g.n[da] || rg.n[db] != me.g.n[db])
+              throw Error("halo exchange: neighbouring boxes are not face-congruent");
+            double *rp = ctx.comm.remote(proc, nbr, (*keys)[f]) + 15;
+            op.ssa = me.g.st(da); op.ssb = me.g.st(db);
+            op.dsa = rg.st(da);   op.dsb = rg.st(db);
+            const long sidx = (ib == 0) ? 1 : me.g.n[d];            // my lo / hi interior plane
+            const long didx = (ib == 0) ? rg.n[d] + 1 : 0;          // the neighbour's hi / lo ghost plane
+            op.src = me.p + sidx * me.g.st(d);
+            op.dst = rp + didx * rg.st(d);
+            mask[d] |= 1u << proc;
+          }
           ops[d].push_back(op);
         }
       }
@@ -105,7 +124,21 @@ void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::ve
   for (int d = 0; d < 3; ++d) local[d].upload(ops[d]);
 }
 
-void Exchange::run(Ctx &ctx, int dir) const { launch_copy_ops(ctx, local[dir]); }
+// one direction: wait until the neighbours are done with the ghost cells (they reached the same
+// exchange), copy / push, then wait for the neighbours' pushes
+void Exchange::run(Ctx &ctx, int dir) const {
+  if (key0 >= 0) ctx.comm.handshake(ctx, CH_READY, mask[dir]);
+  launch_copy_ops(ctx, local[dir]);
+  if (key0 >= 0) ctx.comm.handshake(ctx, CH_ARRIVED, mask[dir]);
+}
+
+void Exchange::run_all(Ctx &ctx) const {   // x, then y, then z (edges/corners propagate)
+  if (key0 >= 0) ctx.comm.handshake(ctx, CH_READY, mask[0] | mask[1] | mask[2]);
+  for (int d = 0; d < 3; ++d) {
+    launch_copy_ops(ctx, local[d]);
+    if (key0 >= 0) ctx.comm.handshake(ctx, CH_ARRIVED, mask[d]);
+  }
+}
 
 void FaceFill::run(Ctx &ctx) const {
   for (int d = 0; d < 3; ++d) launch_face_ops(ctx, ops[d]);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -81,6 +82,7 @@ struct Field3 {
     buf.alloc(g.alloc_elems());
     p = buf.raw + 15;  // so that (1,0,0) is 128-byte aligned
   }
+  void adopt(double *raw) { p = raw + 15; }   // memory owned by the communication arena
 };
 
 // 1-D device array uploaded from host.
@@ -142,6 +144,14 @@ struct DevOps {  // device-resident array of ops
 
 struct Ctx;
 
+// Where the transforms of one box write the right-hand side to / read the solution from: one base
+// pointer per owning process (the wavenumber axis is split into nsplit chunks of `chunk` planes).
+struct FFTRoute {
+  long st[3] = {0, 0, 0};          // strides of the physical directions in the solver arrays
+  double *x[16] = {nullptr}, *b[16] = {nullptr};
+  int chunk = 1, nsplit = 1;
+};
+
 // One ghosted array per local box taking part in an exchange.
 struct ExField {
   int box;       // local box index
@@ -156,12 +166,13 @@ struct NbTable {   // neighbour box ids (global, -1: none) of one local box in t
 };
 struct Exchange {
   DevOps<CopyOp> local[3];
+  unsigned mask[3] = {0, 0, 0};   // peer processes this exchange pushes to / receives from, per direction
+  int key0 = -1;                  // arena key of the first exchanged array (remote neighbours), -1: local only
   // nbs == nullptr: the boxes' physical neighbour tables
-  void build(Ctx &ctx, const std::vector<ExField> &fields, const std::vector<NbTable> *nbs = nullptr);
+  void build(Ctx &ctx, const std::vector<ExField> &fields, const std::vector<NbTable> *nbs = nullptr,
+             const std::vector<int> *keys = nullptr, bool ids_local = false);
   void run(Ctx &ctx, int dir) const;      // one direction
-  void run_all(Ctx &ctx) const {          // x, then y, then z (edges/corners propagate)
-    for (int d = 0; d < 3; ++d) run(ctx, d);
-  }
+  void run_all(Ctx &ctx) const;           // x, then y, then z (edges/corners propagate)
 };
 
 struct FaceFill {
@@ -208,8 +219,10 @@ std::vector<double> r2r_eigenvalues(int n, const char bc[2], bool centered);
 // in -> out along plan.axis over the interior of a ghosted box (in == out allowed); out *= scale
 // in/out address the first interior element; ist/ost are the strides of the physical directions
 // x,y,z in each array (in == out with equal strides is allowed); out *= scale
-void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *in, const long ist[3],
-                 double *out, const long ost[3], double scale);
+// in_split/out_split > 1: that side's transform axis is split into chunks of `chunk` indices, one
+// base pointer per chunk (the owning process' slab, possibly in a peer's memory)
+void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *const *in, int in_split,
+                 const long ist[3], double *const *out, int out_split, const long ost[3], int chunk, double scale);
 
 // ------------------------------------------------------------------------------------------
 // multigrid (mg.cu)
@@ -265,6 +278,7 @@ struct MGSolver {
   DevBuf norms;                    // [2*nq]: sum r^2, sum b^2 per plane
   std::vector<double> h_norms;
   bool use_tiles = false;
+  bool ids_local = false;          // neighbour ids of the solver boxes are solver-box indices (batched: blocks)
   bool plane_local = false;        // fused shared-memory path (planes not split over boxes)
   int first_smem_level = 0;        // first level handled by the one-CTA-per-plane kernel
   std::vector<Field3> x1;          // second x buffer of the tiled levels [level*nbox + box]
@@ -304,6 +318,45 @@ struct Box {
   BoxGeom geom() const;
 };
 
+// ------------------------------------------------------------------------------------------
+// peer communication between the processes of one node (comm.cu): one arena per process holds every
+// array a peer may write or read (field ghost layers, solver slabs, flags); arenas are mapped into
+// each other with CUDA IPC so that halos and transposes are plain loads/stores over NVLink.
+// ------------------------------------------------------------------------------------------
+constexpr int MAXPROC = 16;
+enum CommChannel : int { CH_READY = 0, CH_ARRIVED = 1, CH_FFT = 2, CH_SOLVED = 3, CH_REDUCE = 4, CH_COUNT = 5 };
+enum ArenaKey : int {   // exported arrays: per box (rank) or per block
+  AK_U0 = 0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P, AK_PP, AK_S0 /* .. AK_S0+7 */, AK_SLAB_X = 24, AK_SLAB_B = 25
+};
+struct ArenaRec { int id, key; long long off; };   // id: box rank or block; off: bytes from the arena base
+constexpr int MAXREC = 1024;
+struct CommBlob {   // what every process publishes to the others (fixed size)
+  int proc, nrec;
+  cudaIpcMemHandle_t handle;
+  ArenaRec rec[MAXREC];
+};
+
+struct PeerComm {
+  int nproc = 1, me = 0;
+  bool connected = false;
+  char *arena = nullptr;
+  size_t cap = 0, used = 0;
+  char *peer[MAXPROC] = {nullptr};           // base of every process' arena in this address space
+  std::vector<ArenaRec> recs[MAXPROC];       // published tables
+  long long seq[CH_COUNT] = {0};
+  // layout of the head of every arena: flags[CH_COUNT][MAXPROC] (long long), then red[MAXPROC][4] (double)
+  static constexpr size_t FLAGS_BYTES = CH_COUNT * MAXPROC * sizeof(long long);
+  static constexpr size_t HEAD_BYTES = 4096;
+  void init(int nproc_, int me_, size_t bytes);
+  double *alloc(size_t elems, int id, int key);   // zero-initialised, 256-byte aligned, recorded for export
+  void export_blob(CommBlob &b) const;
+  void connect(const CommBlob *blobs, int n);
+  double *remote(int proc, int id, int key) const;  // address of a published array of process proc
+  // all processes in `mask` signal each other on `ch` and wait (stream-ordered)
+  void handshake(Ctx &ctx, int ch, unsigned mask);
+  void release();
+};
+
 // per-kernel-class device timing (enabled by snac_profile_enable; serialises the stream)
 enum ProfClass : int {
   PC_RK_MOM = 0, PC_HALO_BC, PC_FILLPS, PC_FFT_FWD, PC_MG_SMOOTH0, PC_MG_DOWN0, PC_MG_UP0, PC_MG_COARSE,
@@ -318,10 +371,19 @@ struct Ctx {
   cudaEvent_t prof_ev[2] = {nullptr, nullptr};
   cudaEvent_t timer_ev[2] = {nullptr, nullptr};
   std::vector<int> owner;
+  PeerComm comm;
+  std::vector<snac_box> world;              // every box of the run (info only), indexed by rank
+  std::vector<std::vector<double>> world_dc[3], world_df[3];   // their ghosted 1-D grids
+  std::vector<char> world_set;
   std::vector<std::unique_ptr<Box>> boxes;  // local boxes
   std::vector<int> local_of_rank;           // rank -> local index or -1
   cudaStream_t stream = nullptr;
   bool committed = false;
+  bool ready = false;                       // exchanges and routing built (after snac_comm_connect when nproc > 1)
+  int nq = 1, q0 = 0, q1 = 1;               // wavenumbers of the run and the slab solved by this process
+  std::vector<int> block_index;             // block id -> solver box
+  std::vector<std::array<int, 3>> blocks_lo;
+  std::vector<FFTRoute> route;              // per local box
   int par = 0;                              // which velocity buffer is current
   long long launches = 0;
   std::string err;
@@ -337,6 +399,7 @@ struct Ctx {
   // reductions
   DevBuf red;               // scratch for chkdt/chkdiv
   double *h_red = nullptr;  // pinned
+  double **d_slots = nullptr;
   Box &box_of_rank(int rank);
 };
 

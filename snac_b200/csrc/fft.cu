@@ -14,6 +14,7 @@
 // Every pencil is read once and written once: 16 B per point.
 // Generic path (any n, any kind): dense matrix-vector product against the precomputed n x n
 // transform matrix from shared memory; used for short or non-power-of-two axes.
+#include <algorithm>
 #include <cmath>
 
 #include "common.h"
@@ -148,8 +149,11 @@ void r2r_plan_init(R2RPlan &pl, int axis, int n, const char bc[2], bool centered
 // device
 // ------------------------------------------------------------------------------------------
 struct R2RArgs {
-  const double *in;  // first interior element of the input array
-  double *out;       // first interior element of the output array
+  // first interior element of the input / output array; when the wavenumber axis of that side is
+  // split over processes (nsplit > 1), one base per owning process, chosen by index / chunk
+  const double *inp[16];
+  double *outp[16];
+  int in_split, out_split, chunk;
   long ist[3], ost[3];  // strides of the physical directions x,y,z in the input / output arrays
   int n[3];
   int axis;
@@ -174,6 +178,9 @@ __device__ inline bool pencil_base(const R2RArgs &a, int tile, int p, long &ib, 
 }
 
 // iterate work items (p, t) with the lane-fastest index chosen for coalescing
+#define R2R_IN(t) (a.inp[a.in_split ? (t) / a.chunk : 0])
+#define R2R_OUT(t) (a.outp[a.out_split ? (t) / a.chunk : 0])
+
 #define FOR_ITEMS(LANE_T_, NT_, ...)                                                     \
   {                                                                                      \
     const int tot_ = (NT_) * tp;                                                         \
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(256) r2r_dense_kernel(const R2RArgs a) {
   const int nfull = a.n[a.axis];
   FOR_ITEMS(a.in_lane_t, nfull, {
     long ib, ob;
-    if (pencil_base(a, blockIdx.x, p, ib, ob)) T[t * tpp + p] = a.in[ib + t * isa];
+    if (pencil_base(a, blockIdx.x, p, ib, ob)) T[t * tpp + p] = R2R_IN(t)[ib + t * isa];
   })
   __syncthreads();
   FOR_ITEMS(a.out_lane_t, nfull, {
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(256) r2r_dense_kernel(const R2RArgs a) {
       } else {
         acc = T[t * tpp + p];  // entries beyond the transform length (staggered, q = 1) pass through
       }
-      a.out[ob + t * osa] = acc * a.scale;
+      R2R_OUT(t)[ob + t * osa] = acc * a.scale;
     }
   })
 }
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
     FOR_ITEMS(a.in_lane_t, n, {
       long ib, ob;
       if (pencil_base(a, blockIdx.x, p, ib, ob)) {
-        double v = a.in[ib + t * isa];
+        double v = R2R_IN(t)[ib + t * isa];
         int slot = t;
         if (makhoul) {
           if (sine && (t & 1)) v = -v;
@@ -277,28 +284,28 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
         const C2 xk{e.x + wo.x, e.y + wo.y};        // X[k]
         const C2 xmk{e.x - wo.x, -(e.y - wo.y)};    // X[m-k]
         const int ka = k, kb = m - k;               // the two output wavenumbers (k=0: 0 and m)
-        double *out = a.out + ob;
         const double sc = a.scale;
+#define OUT_AT(idx) R2R_OUT(idx)[ob + (idx) * osa]
         if (!makhoul) {
-          out[ka * osa] = sc * xk.x;
-          if (k > 0) out[(n - ka) * osa] = sc * xk.y;
-          out[kb * osa] = sc * xmk.x;
-          if (k > 0 && kb < m) out[(n - kb) * osa] = sc * xmk.y;
+          OUT_AT(ka) = sc * xk.x;
+          if (k > 0) OUT_AT(n - ka) = sc * xk.y;
+          OUT_AT(kb) = sc * xmk.x;
+          if (k > 0 && kb < m) OUT_AT(n - kb) = sc * xmk.y;
         } else {
           // X_c[k] = 2 Re(e^{-i pi k/2n} V[k]), X_c[n-k] = -2 Im(e^{-i pi k/2n} V[k])
           {
             const double c = __ldg(wd + 2 * ka), s_ = -__ldg(wd + 2 * ka + 1);
             const double v0 = 2.0 * (c * xk.x + s_ * xk.y), v1 = 2.0 * (s_ * xk.x - c * xk.y);
             const int o0 = sine ? (n - 1 - ka) : ka;
-            out[o0 * osa] = sc * v0;
-            if (ka > 0) { const int o1 = sine ? (ka - 1) : (n - ka); out[o1 * osa] = sc * v1; }
+            OUT_AT(o0) = sc * v0;
+            if (ka > 0) { const int o1 = sine ? (ka - 1) : (n - ka); OUT_AT(o1) = sc * v1; }
           }
           {
             const double c = __ldg(wd + 2 * kb), s_ = -__ldg(wd + 2 * kb + 1);
             const double v0 = 2.0 * (c * xmk.x + s_ * xmk.y), v1 = 2.0 * (s_ * xmk.x - c * xmk.y);
             const int o0 = sine ? (n - 1 - kb) : kb;
-            out[o0 * osa] = sc * v0;
-            if (kb < m) { const int o1 = sine ? (kb - 1) : (n - kb); out[o1 * osa] = sc * v1; }
+            OUT_AT(o0) = sc * v0;
+            if (kb < m) { const int o1 = sine ? (kb - 1) : (n - kb); OUT_AT(o1) = sc * v1; }
           }
         }
       }
@@ -309,19 +316,19 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
       long ib, ob;
       const int k = t;
       if (pencil_base(a, blockIdx.x, p, ib, ob)) {
-        const double *in = a.in + ib;
+#define IN_AT(idx) R2R_IN(idx)[ib + (idx) * isa]
         const int kb = m - k;
         C2 xk, xm;  // X[k], X[m-k]
         if (!makhoul) {
-          xk.x = in[k * isa];  xk.y = (k > 0) ? in[(n - k) * isa] : 0.0;
-          xm.x = in[kb * isa]; xm.y = (kb < m) ? in[(n - kb) * isa] : 0.0;
+          xk.x = IN_AT(k);  xk.y = (k > 0) ? IN_AT(n - k) : 0.0;
+          xm.x = IN_AT(kb); xm.y = (kb < m) ? IN_AT(n - kb) : 0.0;
         } else {
           auto getx = [&](int kk) -> C2 {
             const double c = __ldg(wd + 2 * kk), s_ = -__ldg(wd + 2 * kk + 1);
             const int i0 = sine ? (n - 1 - kk) : kk;
-            const double a0 = in[i0 * isa];
+            const double a0 = IN_AT(i0);
             double a1 = 0.0;
-            if (kk > 0) { const int i1 = sine ? (kk - 1) : (n - kk); a1 = in[i1 * isa]; }
+            if (kk > 0) { const int i1 = sine ? (kk - 1) : (n - kk); a1 = IN_AT(i1); }
             return C2{c * a0 + s_ * a1, s_ * a0 - c * a1};
           };
           xk = getx(k);
@@ -368,16 +375,19 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
         if (makhoul) slot = (t & 1) ? (n - 1 - (t >> 1)) : (t >> 1);
         double v = T[slot * tpp + p] * a.scale;
         if (makhoul && sine && (t & 1)) v = -v;
-        a.out[ob + t * osa] = v;
+        R2R_OUT(t)[ob + t * osa] = v;
       }
     })
   }
 }
 
-void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *in, const long ist[3],
-                 double *out, const long ost[3], double scale) {
+void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *const *in, int in_split,
+                 const long ist[3], double *const *out, int out_split, const long ost[3], int chunk, double scale) {
   R2RArgs a;
-  a.in = in; a.out = out;
+  for (int p = 0; p < 16; ++p) { a.inp[p] = nullptr; a.outp[p] = nullptr; }
+  for (int p = 0; p < std::max(in_split, 1); ++p) a.inp[p] = in[p];
+  for (int p = 0; p < std::max(out_split, 1); ++p) a.outp[p] = out[p];
+  a.in_split = in_split > 1; a.out_split = out_split > 1; a.chunk = std::max(chunk, 1);
   for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = ist[d]; a.ost[d] = ost[d]; }
   a.axis = pl.axis;
   a.nt = pl.nt;

@@ -900,6 +900,7 @@ static void build_dir(MGLevelBox &L, int d, bool coupled, const std::vector<doub
 void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
   sboxes = std::move(boxes_);
   fft_dir = batched ? 2 : -1;
+  ids_local = batched;
   const int nl = (int)sboxes.size();
   bool coupled[3];
   for (int d = 0; d < 3; ++d) coupled[d] = (d != fft_dir);
@@ -990,7 +991,7 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
     {
       std::vector<ExField> ef;
       for (int lb = 0; lb < nl; ++lb) ef.push_back(ExField{lb, C.boxes[lb].xp, C.boxes[lb].g});
-      C.ex.build(ctx, ef, &nbt);
+      C.ex.build(ctx, ef, &nbt, nullptr, ids_local);
       for (int d = 0; d < 3; ++d) {
         if (!coupled[d] || !C.ex.local[d].count) continue;
         std::vector<Dev1> tmp(nl);
@@ -1035,7 +1036,7 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
   {
     std::vector<ExField> ef;
     for (int lb = 0; lb < nl; ++lb) ef.push_back(ExField{lb, levels[0]->boxes[lb].xp, levels[0]->boxes[lb].g});
-    levels[0]->ex.build(ctx, ef, &nbt);
+    levels[0]->ex.build(ctx, ef, &nbt, nullptr, ids_local);
   }
   // ---- plane-local fast path -----------------------------------------------------------------
   plane_local = batched && !ctx.prm.mg_generic;
@@ -1046,7 +1047,7 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
     for (int d = 0; d < 2; ++d)
       for (int ib = 0; ib < 2; ++ib) {
         const int nb = sboxes[lb].nb[d][ib];
-        if (nb >= 0 && ctx.local_of_rank[nb] != lb) plane_local = false;   // the plane is split over boxes
+        if (nb >= 0 && (ids_local ? nb : ctx.local_of_rank[nb]) != lb) plane_local = false;   // the plane is split over boxes
       }
   first_smem_level = 0;
   // largest plane handed to the one-CTA-per-plane kernel (it is latency-bound: keep its top level small)

@@ -57,6 +57,9 @@ EXPORTS = {
     "snac_create": (C.c_int, [C.POINTER(snac_params), C.POINTER(C.c_void_p)]),
     "snac_add_box": (C.c_int, [C.c_void_p, C.POINTER(snac_box)]),
     "snac_commit": (C.c_int, [C.c_void_p]),
+    "snac_comm_blob_size": (C.c_size_t, []),
+    "snac_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "snac_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "snac_finalize": (C.c_int, [C.c_void_p]),
     "snac_last_error": (C.c_char_p, [C.c_void_p]),
     "snac_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -62,9 +62,18 @@ class Simulation:
             raise L.SnacError(self.lib.snac_last_error(None).decode())
         self.h = h
         self._keep = []
-        for r in self.ranks:
+        # every box of the run is described to the library; device state is created for the owned ones
+        for r in range(W.nrank):
             self._add_box(r)
         self._chk(self.lib.snac_commit(self.h))
+        if nproc > 1:
+            from .dist import gather_blobs
+            n = int(self.lib.snac_comm_blob_size())
+            buf = C.create_string_buffer(n)
+            self._chk(self.lib.snac_comm_export(self.h, buf))
+            allb = gather_blobs(bytes(buf.raw), nproc)
+            allbuf = C.create_string_buffer(allb, len(allb))
+            self._chk(self.lib.snac_comm_connect(self.h, C.cast(allbuf, C.c_void_p), nproc))
         self.time, self.istep, self.dt, self.dt_cfl = 0.0, 0, 0.0, 0.0
         self.divtot = self.divmax = 0.0
 
