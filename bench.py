@@ -30,7 +30,7 @@ DIMS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (4, 2, 1)}
 
 # algorithmic HBM bytes per grid point and launch of each kernel class
 ALG_BYTES = {"rk_mom": 96.0, "fillps": 32.0, "fft_fwd": 16.0, "fft_bwd": 16.0, "correc_updt_pressure": 72.0,
-             "mg_smooth_l0": 12.0, "mg_restrict_l0": 18.0, "mg_prolong_l0": 18.0, "chkdt_chkdiv": 24.0}
+             "mg_down_l0": 26.0, "mg_up_l0": 26.0}
 
 
 def make_tgv(n, dims, rundir):
@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -123,8 +123,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--n", type=int, default=256, help="cells per direction per GPU")
     ap.add_argument("--n-cpu", type=int, default=96)
@@ -232,9 +232,10 @@ def main():
         nm = g.lib.snac_profile_name(c)
         if nm is None:
             break
-        m, nl = C.c_double(), C.c_longlong()
+        m, nl, un = C.c_double(), C.c_longlong(), C.c_double()
         g.lib.snac_profile_get(g.h, c, C.byref(m), C.byref(nl))
-        classes[nm.decode()] = (m.value / nprof, nl.value / nprof)
+        g.lib.snac_profile_units(g.h, c, C.byref(un))
+        classes[nm.decode()] = (m.value / nprof, nl.value / nprof, un.value / nprof)
         c += 1
     g.lib.snac_profile_enable(g.h, 0)
     if rank == 0:
@@ -246,21 +247,27 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         tot_prof = sum(v[0] for v in classes.values())
-        npts_gpu = float(args.n) ** 3
         table = {}
-        for nm, (m, nl) in classes.items():
+        for nm, (m, nl, un) in classes.items():
             ent = {"ms_per_step": round(m, 4), "launches_per_step": nl, "share": round(m / tot_prof, 4) if tot_prof else None}
-            if nm in ALG_BYTES and nl > 0 and m > 0:
-                ent["achieved_gbs"] = round(ALG_BYTES[nm] * npts_gpu * nl / (m * 1e-3) / 1e9, 1)
+            if nm in ALG_BYTES and un > 0 and m > 0:
+                ent["points_per_step"] = un
+                ent["achieved_gbs"] = round(ALG_BYTES[nm] * un / (m * 1e-3) / 1e9, 1)
             table[nm] = ent
         dom = max((k for k in classes if k in ALG_BYTES), key=lambda k: classes[k][0])
-        m, nl = classes[dom]
-        ach = ALG_BYTES[dom] * npts_gpu * nl / (m * 1e-3) / 1e9
+        m, nl, un = classes[dom]
+        ach = ALG_BYTES[dom] * un / (m * 1e-3) / 1e9
+        traffic = None
+        try:   # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except OSError:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None,
+                "frac": round(ach / peak, 4), "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                "bytes_per_launch": ALG_BYTES[dom] * npts_gpu, "avg_launch_ms": round(m / nl, 5),
-                "classes": table}
+                "bytes_per_launch": round(ALG_BYTES[dom] * un / nl, 1), "avg_launch_ms": round(m / nl, 5),
+                "algorithmic_bytes_per_point": ALG_BYTES[dom], "classes": table}
         line = {"metric": "Mpts*step/s (RK3 step of the pressure-correction pipeline)", "value": round(value, 3),
                 "unit": "Mpts*step/s", "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(t_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",

@@ -162,6 +162,9 @@ SNAC_API int snac_solver_mean_iters(snac_handle *h, double *mean_iters);
  * to measure throughput.  Classes are numbered from 0; snac_profile_name returns NULL past the end. */
 SNAC_API int snac_profile_enable(snac_handle *h, int on);
 SNAC_API int snac_profile_get(snac_handle *h, int cls, double *ms, long long *launches);
+/* grid points processed by the launches of a class (the solver kernels count only the wavenumber
+ * planes that were still iterating) */
+SNAC_API int snac_profile_units(snac_handle *h, int cls, double *points);
 SNAC_API const char *snac_profile_name(int cls);
 /* CUDA-event stopwatch on the handle's stream (start records, stop records + waits). */
 SNAC_API int snac_timer_start(snac_handle *h);

@@ -445,7 +445,9 @@ static void transfer(Ctx &ctx, int rank, int field, double *host, bool up) {
 // ---- pieces of the sub-step ------------------------------------------------------------------
 static void do_rk_mom(Ctx &ctx, int irk, double dt) {
   if (irk < 1 || irk > 3) throw Error("rk_mom: irk must be 1, 2 or 3");
-  ProfScope ps(ctx, PC_RK_MOM);
+  double pts = 0.0;
+  for (auto &b : ctx.boxes) pts += (double)b->g.n[0] * b->g.n[1] * b->g.n[2];
+  ProfScope ps(ctx, PC_RK_MOM, pts);
   for (auto &b : ctx.boxes) launch_rk_mom(ctx, *b, irk, dt);
   ctx.par = 1 - ctx.par;
 }
@@ -466,7 +468,9 @@ static void do_boundp(Ctx &ctx, int field) {
 static void do_fft(Ctx &ctx, int dir) {
   if (ctx.prm.fft_axis == 0) throw Error("fft: the handle was created with fft_axis = 0");
   if (!ctx.ready) throw Error("snac_comm_connect has not been called");
-  ProfScope ps(ctx, dir > 0 ? PC_FFT_FWD : PC_FFT_BWD);
+  double pts = 0.0;
+  for (auto &b : ctx.boxes) pts += (double)b->g.n[0] * b->g.n[1] * b->g.n[2];
+  ProfScope ps(ctx, dir > 0 ? PC_FFT_FWD : PC_FFT_BWD, pts);
   for (int lb = 0; lb < (int)ctx.boxes.size(); ++lb) {
     Box &b = *ctx.boxes[lb];
     const FFTRoute &R = ctx.route[lb];
@@ -537,8 +541,10 @@ static void substep(Ctx &ctx, int irk, double dt) {
     throw Error("snac_step: scalar transport / implicit diffusion are not available in this build");
   do_rk_mom(ctx, irk, dt);
   do_bounduvw(ctx, false);
+  double pts = 0.0;
+  for (auto &b : ctx.boxes) pts += (double)b->g.n[0] * b->g.n[1] * b->g.n[2];
   {
-    ProfScope ps(ctx, PC_FILLPS);
+    ProfScope ps(ctx, PC_FILLPS, pts);
     for (auto &b : ctx.boxes) launch_fillps_bc(ctx, *b, dtrk);
   }
   if (ctx.prm.fft_axis > 0) {
@@ -550,7 +556,7 @@ static void substep(Ctx &ctx, int irk, double dt) {
   }
   do_boundp(ctx, SNAC_FIELD_PP);
   {
-    ProfScope ps(ctx, PC_CORREC);
+    ProfScope ps(ctx, PC_CORREC, pts);
     for (auto &b : ctx.boxes) launch_correc_updt(ctx, *b, dtrk, alpha, true, true);
   }
   do_bounduvw(ctx, true);
@@ -763,7 +769,7 @@ int snac_profile_enable(snac_handle *h, int on) {
   SNAC_TRY(h, {
     SNAC_CUDA(cudaStreamSynchronize(h->ctx.stream));
     h->ctx.prof_on = on != 0;
-    if (on) for (int c = 0; c < PC_COUNT; ++c) { h->ctx.prof_ms[c] = 0.0; h->ctx.prof_n[c] = 0; }
+    if (on) for (int c = 0; c < PC_COUNT; ++c) { h->ctx.prof_ms[c] = 0.0; h->ctx.prof_n[c] = 0; h->ctx.prof_units[c] = 0.0; }
   })
 }
 int snac_profile_get(snac_handle *h, int cls, double *ms, long long *launches) {
@@ -771,6 +777,12 @@ int snac_profile_get(snac_handle *h, int cls, double *ms, long long *launches) {
     if (cls < 0 || cls >= PC_COUNT) throw Error("snac_profile_get: class out of range");
     if (ms) *ms = h->ctx.prof_ms[cls];
     if (launches) *launches = h->ctx.prof_n[cls];
+  })
+}
+int snac_profile_units(snac_handle *h, int cls, double *points) {
+  SNAC_TRY(h, {
+    if (cls < 0 || cls >= PC_COUNT) throw Error("snac_profile_units: class out of range");
+    if (points) *points = h->ctx.prof_units[cls];
   })
 }
 const char *snac_profile_name(int cls) {

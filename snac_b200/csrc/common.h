@@ -368,6 +368,7 @@ struct Ctx {
   bool prof_on = false;
   double prof_ms[PC_COUNT] = {0};
   long long prof_n[PC_COUNT] = {0};
+  double prof_units[PC_COUNT] = {0};   // grid points processed (active planes only for the solver kernels)
   cudaEvent_t prof_ev[2] = {nullptr, nullptr};
   cudaEvent_t timer_ev[2] = {nullptr, nullptr};
   std::vector<int> owner;
@@ -407,8 +408,8 @@ struct ProfScope {
   Ctx &c;
   int cls;
   long long l0;
-  ProfScope(Ctx &ctx, int cls_) : c(ctx), cls(cls_), l0(ctx.launches) {
-    if (c.prof_on) cudaEventRecord(c.prof_ev[0], c.stream);
+  ProfScope(Ctx &ctx, int cls_, double units = 0.0) : c(ctx), cls(cls_), l0(ctx.launches) {
+    if (c.prof_on) { c.prof_units[cls] += units; cudaEventRecord(c.prof_ev[0], c.stream); }
   }
   ~ProfScope() {
     if (!c.prof_on) return;

@@ -1181,8 +1181,17 @@ struct Cycle {
     return which == 0 ? S.levels[l]->boxes[lb].xp : S.x1[(size_t)l * S.levels[0]->boxes.size() + lb].p;
   }
   // down: xbuf(l,0) -> xbuf(l,1), residual restricted into level l+1's b
+  double active_points(int l) {   // profile mode only: planes still iterating x plane size
+    if (!ctx.prof_on) return 0.0;
+    int cnt = S.nq;
+    cudaMemcpyAsync(&cnt, S.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream);
+    cudaStreamSynchronize(ctx.stream);
+    double cells = 0.0;
+    for (auto &b : S.levels[l]->boxes) cells += (double)b.g.n[0] * b.g.n[1];
+    return cells * cnt;
+  }
   void plane_down(int l, bool norms, bool want_b) {
-    ProfScope ps(ctx, l == 0 ? PC_MG_DOWN0 : PC_MG_COARSE);
+    ProfScope ps(ctx, l == 0 ? PC_MG_DOWN0 : PC_MG_COARSE, l == 0 ? active_points(0) : 0.0);
     MGLevel &F = *S.levels[l];
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
       PLevel P = plevel(l, (int)lb);
@@ -1203,7 +1212,7 @@ struct Cycle {
     }
   }
   void plane_up(int l) {
-    ProfScope ps(ctx, l == 0 ? PC_MG_UP0 : PC_MG_COARSE);
+    ProfScope ps(ctx, l == 0 ? PC_MG_UP0 : PC_MG_COARSE, l == 0 ? active_points(0) : 0.0);
     MGLevel &F = *S.levels[l];
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
       PLevel P = plevel(l, (int)lb);

@@ -82,6 +82,7 @@ EXPORTS = {
     "snac_solver_mean_iters": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "snac_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "snac_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "snac_profile_units": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "snac_profile_name": (C.c_char_p, [C.c_int]),
     "snac_timer_start": (C.c_int, [C.c_void_p]),
     "snac_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
