@@ -154,6 +154,88 @@ static void alloc_field(Ctx &ctx, Field3 &f, const Grid3 &g, int id, int key) {
   else f.alloc(g);
 }
 
+// Implicit diffusion (IMPDIFF): one Helmholtz problem per velocity component on its own staggered
+// grid and one per scalar (src/main.f90:770-886).  The operators are strongly diagonally dominant
+// (diagonal shift alphai = -2/(nu dtrk)), and the staggered unknowns do not coarsen by cell pairs,
+// so they are solved on a single level with red-black Gauss-Seidel sweeps; the shifted diagonal is a
+// kernel argument, so nothing is re-assembled when dt changes (the reference re-creates and
+// re-sets-up its HYPRE solver on every call, src/solve_helmholtz.f90:85-86,134-135).
+static double helm_bc_coef(const Box &b, int d, int ib, char c, double bc, bool centered, int nhi, const std::vector<double> &d1,
+                           const std::vector<double> &d2, const int periods[3]) {
+  if (!b.info.is_bound[d][ib] || periods[d] != 0) return 0.0;
+  if (ib == 1 && nhi == 1) return 0.0;   // the reference loop visits i==lo only (ib=0)
+  double factor = 0.0;
+  const double dl = centered ? b.info.dl[d][ib] : b.info.dlf[d][ib];
+  if (c == 'N') factor = (ib == 0 ? 1.0 : -1.0) * dl * bc;
+  else if (c == 'D') factor = centered ? -2.0 * bc : -1.0 * bc;
+  const int qqq = centered ? 0 : 1;
+  const int i = (ib == 0) ? 1 : nhi;
+  return factor * d2[i] / (d1[i - (1 - ib) + qqq] * d2[i]);   // src/solver.f90:125 (3-D weight)
+}
+
+static void setup_impdiff(Ctx &ctx) {
+  if (ctx.prm.fft_axis > 0) throw Error("implicit diffusion together with FFT_AXIS is not available in this build");
+  if (ctx.comm.nproc > 1) throw Error("implicit diffusion on several processes is not available in this build");
+  const int nl = (int)ctx.boxes.size();
+  auto fold_sign = [](char c, bool centered) {
+    if (c == 'N') return 1.0;
+    if (c == 'D') return centered ? -1.0 : 0.0;
+    throw Error("a physical boundary must be 'D' or 'N'");
+  };
+  for (int c = 0; c < 3; ++c)
+    for (int par = 0; par < 2; ++par) {
+      std::vector<SBox> sb(nl);
+      for (int lb = 0; lb < nl; ++lb) {
+        Box &b = *ctx.boxes[lb];
+        SBox &s = sb[lb];
+        for (int d = 0; d < 3; ++d) {
+          const bool cen = d != c;
+          s.n[d] = b.g.n[d] - ((!cen && b.info.is_bound[d][1]) ? 1 : 0);   // hiu/hiv/hiw, src/main.f90:774-776
+          s.d1[d] = cen ? b.h_dc[d] : b.h_df[d];
+          s.d2[d] = cen ? b.h_df[d] : b.h_dc[d];
+          s.qqq[d] = cen ? 0 : 1;
+          for (int ib = 0; ib < 2; ++ib) {
+            s.nb[d][ib] = b.info.nb[d][ib];
+            s.phys[d][ib] = b.info.is_bound[d][ib] && ctx.prm.periods[d] == 0;
+            s.sgn[d][ib] = s.phys[d][ib] ? fold_sign(b.info.cbcvel[c][d][ib], cen) : 0.0;
+            if (par == 0)
+              b.cbu[c][d][ib] = helm_bc_coef(b, d, ib, b.info.cbcvel[c][d][ib], b.info.bcvel[c][d][ib], cen, s.n[d], s.d1[d], s.d2[d],
+                                             ctx.prm.periods);
+          }
+        }
+        s.x = (c == 0 ? b.u[par] : (c == 1 ? b.v[par] : b.w[par])).p;
+        s.b = b.rhs.p;
+        s.sy = b.g.sy; s.sz = b.g.sz;
+      }
+      ctx.usolver[c][par].reset(new MGSolver);
+      ctx.usolver[c][par]->setup(ctx, std::move(sb), false, 1);
+    }
+  for (int is = 0; is < ctx.prm.nscal; ++is) {
+    std::vector<SBox> sb(nl);
+    for (int lb = 0; lb < nl; ++lb) {
+      Box &b = *ctx.boxes[lb];
+      SBox &s = sb[lb];
+      for (int d = 0; d < 3; ++d) {
+        s.n[d] = b.g.n[d];
+        s.d1[d] = b.h_dc[d];
+        s.d2[d] = b.h_df[d];
+        for (int ib = 0; ib < 2; ++ib) {
+          s.nb[d][ib] = b.info.nb[d][ib];
+          s.phys[d][ib] = b.info.is_bound[d][ib] && ctx.prm.periods[d] == 0;
+          s.sgn[d][ib] = s.phys[d][ib] ? fold_sign(b.info.cbcscal[is][d][ib], true) : 0.0;
+          b.cbs[is][d][ib] = helm_bc_coef(b, d, ib, b.info.cbcscal[is][d][ib], b.info.bcscal[is][d][ib], true, s.n[d], s.d1[d],
+                                          s.d2[d], ctx.prm.periods);
+        }
+      }
+      s.x = b.s[is].p;
+      s.b = b.rhs.p;
+      s.sy = b.g.sy; s.sz = b.g.sz;
+    }
+    ctx.ssolver[is].reset(new MGSolver);
+    ctx.ssolver[is]->setup(ctx, std::move(sb), false, 1);
+  }
+}
+
 static void finish_setup(Ctx &ctx);
 
 static void commit(Ctx &ctx) {
@@ -207,6 +289,7 @@ static void commit(Ctx &ctx) {
     else { alloc_field(ctx, b.pp, b.g, r, AK_PP); b.stage.alloc(b.g); }
     b.du.alloc(b.g); b.dv.alloc(b.g); b.dw.alloc(b.g);
     for (int s = 0; s < ctx.prm.nscal; ++s) { alloc_field(ctx, b.s[s], b.g, r, AK_S0 + s); b.ds[s].alloc(b.g); }
+    if (ctx.prm.nscal > 0) { b.scr0.alloc(b.g); b.scr1.alloc(b.g); }
     compute_bc_rhs(ctx, b);
   }
   // transforms (fftini for the pressure, src/main.f90:735)
@@ -296,6 +379,7 @@ static void commit(Ctx &ctx) {
     }
     S.setup(ctx, std::move(sb), batched);
   }
+  if (ctx.prm.impdiff) setup_impdiff(ctx);
   ctx.red.alloc(8);
   SNAC_CUDA(cudaMallocHost(&ctx.h_red, 4 * MAXPROC * sizeof(double)));
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -533,13 +617,60 @@ static void do_chk(Ctx &ctx, bool want_dt, double *out3) {
   }
 }
 
+static const double RKC[3][2] = {{32.0 / 60.0, 0.0}, {25.0 / 60.0, -17.0 / 60.0}, {45.0 / 60.0, -25.0 / 60.0}};
+
+// rk_scal + bulk_forcing_s for one scalar (src/main.f90:910-913)
+static void do_rk_scal(Ctx &ctx, int irk, double dt, int is) {
+  if (is < 0 || is >= ctx.prm.nscal) throw Error("rk_scal: scalar index out of range");
+  if (irk < 1 || irk > 3) throw Error("rk_scal: irk must be 1, 2 or 3");
+  const double f1 = RKC[irk - 1][0] * dt, f2 = RKC[irk - 1][1] * dt, f12 = f1 + f2;
+  const bool forced = ctx.prm.is_sforced[is] != 0;
+  for (auto &b : ctx.boxes) launch_scal_rhs(ctx, *b, is, 1.0 / ctx.prm.alphai[is]);
+  double *d_sum = ctx.red.raw + 4;
+  if (forced) SNAC_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), ctx.stream));
+  for (auto &b : ctx.boxes) launch_scal_update(ctx, *b, is, f1, f2, f12, d_sum);
+  double f = 0.0;
+  if (forced) {   // bulk_mean_s (src/scal.f90:156-179)
+    if (ctx.comm.nproc > 1) throw Error("forced scalars on several processes are not available in this build");
+    SNAC_CUDA(cudaMemcpyAsync(ctx.h_red, d_sum, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+    f = ctx.prm.scalf[is] - ctx.h_red[0] / ctx.prm.vol_all;
+  }
+  if (ctx.prm.impdiff || forced)
+    for (auto &b : ctx.boxes) launch_scal_finish(ctx, *b, is, f12, f);
+  ctx.fs[is] += f;
+}
+
+// solve_impdiff_field_3d (src/solve_helmholtz.f90:102-138) for a scalar or a velocity component
+static void do_helmholtz(Ctx &ctx, MGSolver &S, int comp /* 0..2 velocity, -1-is scalar */, double alphai) {
+  const int nl = (int)ctx.boxes.size();
+  for (int lb = 0; lb < nl; ++lb) {
+    Box &b = *ctx.boxes[lb];
+    const double *wq[3];
+    int nhi[3];
+    for (int d = 0; d < 3; ++d) {
+      wq[d] = (comp >= 0 && d == comp) ? b.dc[d].p() : b.df[d].p();
+      nhi[d] = S.sboxes[lb].n[d];
+    }
+    const double *fld = S.levels[0]->boxes[lb].xp;
+    launch_helm_rhs(ctx, b, fld, wq, comp >= 0 ? b.cbu[comp] : b.cbs[-1 - comp], nhi, alphai);
+  }
+  S.alpha = alphai;
+  S.solve(ctx);
+}
+
 static void substep(Ctx &ctx, int irk, double dt) {
-  static const double RK[3][2] = {{32.0 / 60.0, 0.0}, {25.0 / 60.0, -17.0 / 60.0}, {45.0 / 60.0, -25.0 / 60.0}};
-  const double dtrk = (RK[irk - 1][0] + RK[irk - 1][1]) * dt;
+  const double dtrk = (RKC[irk - 1][0] + RKC[irk - 1][1]) * dt;
   const double alpha = -ctx.prm.visc * dtrk / 2.0;
-  if (ctx.prm.nscal > 0 || ctx.prm.impdiff)
-    throw Error("snac_step: scalar transport / implicit diffusion are not available in this build");
+  if (!ctx.ready) throw Error("snac_comm_connect has not been called");
+  for (int is = 0; is < ctx.prm.nscal; ++is) {   // src/main.f90:908-937
+    do_rk_scal(ctx, irk, dt, is);
+    if (ctx.prm.impdiff) do_helmholtz(ctx, *ctx.ssolver[is], -1 - is, 1.0 / (-(1.0 / ctx.prm.alphai[is]) * dtrk / 2.0));
+    do_boundp(ctx, SNAC_FIELD_S0 + is);
+  }
   do_rk_mom(ctx, irk, dt);
+  if (ctx.prm.impdiff)   // src/main.f90:947-994
+    for (int c = 0; c < 3; ++c) do_helmholtz(ctx, *ctx.usolver[c][ctx.par], c, 1.0 / alpha);
   do_bounduvw(ctx, false);
   double pts = 0.0;
   for (auto &b : ctx.boxes) pts += (double)b->g.n[0] * b->g.n[1] * b->g.n[2];
@@ -697,9 +828,7 @@ int snac_download(snac_handle *h, int rank, int field, double *host) {
 }
 
 int snac_rk_mom(snac_handle *h, int irk, double dt) { SNAC_TRY(h, do_rk_mom(h->ctx, irk, dt)) }
-int snac_rk_scal(snac_handle *h, int, double, int) {
-  SNAC_TRY(h, throw Error("snac_rk_scal: scalar transport is not available in this build"))
-}
+int snac_rk_scal(snac_handle *h, int irk, double dt, int iscal) { SNAC_TRY(h, do_rk_scal(h->ctx, irk, dt, iscal)) }
 int snac_bounduvw(snac_handle *h, int is_correc) { SNAC_TRY(h, do_bounduvw(h->ctx, is_correc != 0)) }
 int snac_boundp(snac_handle *h, int field) { SNAC_TRY(h, do_boundp(h->ctx, field)) }
 int snac_fillps(snac_handle *h, double dtrk) {

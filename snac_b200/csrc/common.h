@@ -264,6 +264,8 @@ struct SBox {
   std::vector<double> d1[3], d2[3]; // ghosted spacings: between unknowns / cell widths
   std::vector<double> lam;          // ghosted eigenvalues/dl^2 along direction 2 (batched only)
   double *x = nullptr, *b = nullptr; // level-0 arrays if they alias context fields (3-D solve)
+  long sy = 0, sz = 0;              // their strides when they differ from Grid3::make(n) (shortened staggered ranges)
+  int qqq[3] = {0, 0, 0};           // 1: unknowns staggered along that direction (src/solver.f90:66-67)
 };
 
 struct MGSolver {
@@ -289,7 +291,7 @@ struct MGSolver {
   int last_iters = 0;
   double last_relres = 0.0;
   double alpha = 0.0;              // extra diagonal shift (IMPDIFF: alphai)
-  void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched);
+  void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched, int max_levels = 24);
   void solve(Ctx &ctx);
   const Grid3 &grid0(int lb) const { return levels[0]->boxes[lb].g; }
   double *xcur(int lb) const { return levels[0]->boxes[lb].xp; }
@@ -309,6 +311,9 @@ struct Box {
   Field3 stage;             // staging array for transfers of spectral fields (batched solves)
   Field3 du, dv, dw;        // d?dtrko
   Field3 s[SNAC_MAX_SCAL], ds[SNAC_MAX_SCAL];
+  Field3 scr0, scr1;        // scratch of rk_scal (new RHS, diffusion term)
+  double cbu[3][3][2];      // boundary RHS coefficients of the velocity Helmholtz problems [comp][idir][ib]
+  double cbs[SNAC_MAX_SCAL][3][2];
   // Poisson RHS: weights (cell width, or 1 along the transform axis), 1/width along the transform
   // axis (else 1), and the boundary coefficient of init_bc_rhs per face
   Dev1 wq[3], gq[3];
@@ -397,6 +402,9 @@ struct Ctx {
   // transforms and solvers
   R2RPlan plan_p;
   MGSolver psolver;
+  std::unique_ptr<MGSolver> usolver[3][2];          // IMPDIFF: [component][velocity buffer]
+  std::unique_ptr<MGSolver> ssolver[SNAC_MAX_SCAL];
+  double fs[SNAC_MAX_SCAL] = {0};                   // accumulated scalar forcing (src/main.f90:913)
   // reductions
   DevBuf red;               // scratch for chkdt/chkdiv
   double *h_red = nullptr;  // pinned
@@ -429,6 +437,11 @@ void launch_fillps_bc(Ctx &ctx, Box &b, double dtrk);
 void launch_updt_rhs(Ctx &ctx, Box &b);
 void launch_correc_updt(Ctx &ctx, Box &b, double dtrk, double alpha, bool do_correc, bool do_updt);
 void launch_chk(Ctx &ctx, Box &b, double *d_out /* [4]: dti_max, divtot, divmax, - */);
+void launch_helm_rhs(Ctx &ctx, Box &b, const double *fld, const double *const wq[3], const double cb[3][2], const int nhi[3],
+                     double alphai);
+void launch_scal_rhs(Ctx &ctx, Box &b, int is, double alpha);
+void launch_scal_update(Ctx &ctx, Box &b, int is, double f1, double f2, double f12, double *d_sum);
+void launch_scal_finish(Ctx &ctx, Box &b, int is, double f12, double f);
 void compute_bc_rhs(Ctx &ctx, Box &b);
 
 }  // namespace snac

@@ -874,14 +874,14 @@ static MGKernelBox kbox(const MGSolver &S, const MGLevelBox &L, int lb, const bo
 // builds am/ap/ad/w of one direction of one box from ghosted spacings d1 (between unknowns) and
 // d2 (cell widths), folding physical boundary conditions into the diagonal
 static void build_dir(MGLevelBox &L, int d, bool coupled, const std::vector<double> &d1, const std::vector<double> &d2,
-                      const double sgn[2], const bool phys[2]) {
+                      const double sgn[2], const bool phys[2], int qqq = 0) {
   const int n = L.g.n[d];
   std::vector<double> am(n + 2, 0.0), ap(n + 2, 0.0), ad(n + 2, 0.0), w(n + 2, 1.0);
   if (coupled) {
     for (int i = 0; i <= n + 1; ++i) w[i] = d2[i];
     for (int i = 1; i <= n; ++i) {
-      am[i] = 1.0 / d1[i - 1];
-      ap[i] = 1.0 / d1[i];
+      am[i] = 1.0 / d1[i - 1 + qqq];   // src/solver.f90:289-297 (index shift of staggered unknowns)
+      ap[i] = 1.0 / d1[i + qqq];
       ad[i] = -(am[i] + ap[i]);
     }
     if (phys[0]) { ad[1] += sgn[0] * am[1]; am[1] = 0.0; }
@@ -897,7 +897,7 @@ static void build_dir(MGLevelBox &L, int d, bool coupled, const std::vector<doub
   L.sam[d].upload(sam); L.sap[d].upload(sap); L.se[d].upload(se); L.srw[d].upload(srw);
 }
 
-void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
+void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max_levels) {
   sboxes = std::move(boxes_);
   fft_dir = batched ? 2 : -1;
   ids_local = batched;
@@ -933,12 +933,13 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
       SBox &sb = sboxes[lb];
       MGLevelBox &L = L0.boxes[lb];
       L.g = Grid3::make(sb.n[0], sb.n[1], sb.n[2]);
+      if (sb.sy) { L.g.sy = sb.sy; L.g.sz = sb.sz; }
       if (sb.x && sb.b) { L.xp = sb.x; L.bp = sb.b; }
       else {
         x0[lb].alloc(L.g); b0[lb].alloc(L.g);
         L.xp = x0[lb].p; L.bp = b0[lb].p;
       }
-      for (int d = 0; d < 3; ++d) build_dir(L, d, coupled[d], sb.d1[d], sb.d2[d], sb.sgn[d], sb.phys[d]);
+      for (int d = 0; d < 3; ++d) build_dir(L, d, coupled[d], sb.d1[d], sb.d2[d], sb.sgn[d], sb.phys[d], sb.qqq[d]);
     }
   }
   // coarser levels
@@ -964,7 +965,7 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched) {
       if (!coupled[d] || all_one[d]) continue;
       if (hsum[d] / ncnt[d] < 1.5 * hmin) { co[d] = 1; any = true; }
     }
-    if (!any || levels.size() >= 24) break;
+    if (!any || (int)levels.size() >= max_levels) break;
     for (int d = 0; d < 3; ++d) F.coarsen[d] = co[d];
     levels.emplace_back(new MGLevel);
     MGLevel &Fm = *levels[levels.size() - 2];

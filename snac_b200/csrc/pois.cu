@@ -18,7 +18,10 @@ struct PoisArgs {
   const double *gq[3];  // 1, or 1/width along the transform axis
   double cb[3][2];      // boundary RHS coefficient per face (0: none)
   double rdt;
-  int do_fill, do_bc;
+  int do_fill, do_bc;   // do_fill = 2: rhs = alphai * weight * fld (Helmholtz right-hand side)
+  const double *fld;
+  double alphai;
+  int nhi[3];           // range on which the boundary terms are added (shortened for staggered unknowns)
 };
 
 __global__ void __launch_bounds__(256) fillps_kernel(const PoisArgs a) {
@@ -29,7 +32,9 @@ __global__ void __launch_bounds__(256) fillps_kernel(const PoisArgs a) {
   const long sy = a.g.sy, sz = a.g.sz, c = i + sy * j + sz * k;
   const double wx = __ldg(a.wq[0] + i), wy = __ldg(a.wq[1] + j), wz = __ldg(a.wq[2] + k);
   double val;
-  if (a.do_fill) {
+  if (a.do_fill == 2) {
+    val = a.alphai * wx * wy * wz * a.fld[c];   // src/solve_helmholtz.f90:121-129
+  } else if (a.do_fill) {
     const double du = a.u[c] - a.u[c - 1], dv = a.v[c] - a.v[c - sy], dw = a.w[c] - a.w[c - sz];
     val = (dw * __ldg(a.gq[2] + k) * wx * wy + dv * __ldg(a.gq[1] + j) * wx * wz +
            du * __ldg(a.gq[0] + i) * wy * wz) * a.rdt;
@@ -37,12 +42,16 @@ __global__ void __launch_bounds__(256) fillps_kernel(const PoisArgs a) {
     val = a.rhs[c];
   }
   if (a.do_bc) {
-    if (i == 1) val += a.cb[0][0] * wy * wz;
-    if (i == a.g.n[0]) val += a.cb[0][1] * wy * wz;
-    if (j == 1) val += a.cb[1][0] * wx * wz;
-    if (j == a.g.n[1]) val += a.cb[1][1] * wx * wz;
-    if (k == 1) val += a.cb[2][0] * wx * wy;
-    if (k == a.g.n[2]) val += a.cb[2][1] * wx * wy;
+    // updt_rhs acts on lo:hi of the (possibly shortened) unknown range (src/bound.f90:543-585)
+    const bool in = i <= a.nhi[0] && j <= a.nhi[1] && k <= a.nhi[2];
+    if (in) {
+      if (i == 1) val += a.cb[0][0] * wy * wz;
+      if (i == a.nhi[0]) val += a.cb[0][1] * wy * wz;
+      if (j == 1) val += a.cb[1][0] * wx * wz;
+      if (j == a.nhi[1]) val += a.cb[1][1] * wx * wz;
+      if (k == 1) val += a.cb[2][0] * wx * wy;
+      if (k == a.nhi[2]) val += a.cb[2][1] * wx * wy;
+    }
   }
   a.rhs[c] = val;
 }
@@ -70,6 +79,27 @@ static void fill_common(Ctx &ctx, Box &b, double dtrk, int do_fill, int do_bc) {
   a.rdt = do_fill ? 1.0 / dtrk : 0.0;
   a.do_fill = do_fill;
   a.do_bc = do_bc;
+  a.fld = nullptr; a.alphai = 0.0;
+  for (int d = 0; d < 3; ++d) a.nhi[d] = b.g.n[d];
+  dim3 blk = pick_block(b.g), grd = grid_for(blk, b.g.n[0], b.g.n[1], b.g.n[2]);
+  fillps_kernel<<<grd, blk, 0, ctx.stream>>>(a);
+  ctx.launches++;
+  SNAC_CUDA(cudaGetLastError());
+}
+
+// right-hand side of an implicit-diffusion Helmholtz problem into the box's rhs array
+void launch_helm_rhs(Ctx &ctx, Box &b, const double *fld, const double *const wq[3], const double cb[3][2], const int nhi[3],
+                     double alphai) {
+  PoisArgs a;
+  a.g = b.geom();
+  a.u = a.v = a.w = nullptr;
+  a.rhs = b.rhs.p;
+  for (int d = 0; d < 3; ++d) {
+    a.wq[d] = wq[d]; a.gq[d] = nullptr;
+    a.cb[d][0] = cb[d][0]; a.cb[d][1] = cb[d][1];
+    a.nhi[d] = nhi[d];
+  }
+  a.rdt = 0.0; a.do_fill = 2; a.do_bc = 1; a.fld = fld; a.alphai = alphai;
   dim3 blk = pick_block(b.g), grd = grid_for(blk, b.g.n[0], b.g.n[1], b.g.n[2]);
   fillps_kernel<<<grd, blk, 0, ctx.stream>>>(a);
   ctx.launches++;

@@ -102,14 +102,14 @@ def duct_blocks_case(rundir, n=(8, 8, 8), **kw):
     write_case(rundir, blocks, **kw)
 
 
-def make(kind, rundir, fft_axis=0, **kw):
+def make(kind, rundir, fft_axis=0, impdiff=False, boussinesq=False, **kw):
     # the transform axis must not be decomposed (reference src/sanity.f90:75-79)
     if kind == "channel" and fft_axis == 1:
         kw.setdefault("dims", (1, 2, 2))
     if kind == "cavity" and fft_axis == 2:
         kw.setdefault("dims", (2, 1, 1))
     {"channel": channel_case, "cavity": cavity_case, "tgv": tgv_case, "duct": duct_blocks_case}[kind](rundir, **kw)
-    return setup_case(rundir, fft_axis=fft_axis)
+    return setup_case(rundir, fft_axis=fft_axis, impdiff=impdiff, boussinesq=boussinesq)
 
 
 def random_fields(case, seed=0, amp=1.0):
