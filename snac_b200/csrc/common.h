@@ -233,8 +233,22 @@ struct MGLevelBox {
   double *xp = nullptr, *bp = nullptr;
   Dev1 am[3], ap[3], ad[3], w[3];   // ghosted 1-D coefficient arrays (index 0..n+1)
   Dev1 sam[3], sap[3], se[3], srw[3];  // scaled by the cell width: am/w, ap/w, ad/w, 1/w
+  Dev1 tab[3];                         // packed {-am/w, -ap/w, ad/w, w, 1/w, 0, 0, 0} per index; entry 0 = outside cell (mg_ring.cu)
   std::vector<double> h_w[3];       // host copy of cell widths (for coarsening)
 };
+
+// one level of a plane-local batched 2-D problem as seen by the prefetch-ring kernels (mg_ring.cu)
+struct RLevel {
+  int n1, n2;
+  int sy; long sz;           // row / plane strides of this level's arrays
+  const double *ctab, *rtab; // packed coefficient tables of directions 0 and 1 (MGLevelBox::tab)
+  int c1, c2;                // directions coarsened towards the next level
+  int per1, per2;            // periodic wrap onto the box itself
+};
+void launch_ring_down(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb, long csy,
+                      long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact);
+void launch_ring_up(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, const double *cx, long csy,
+                    long csz, const double *lamq, double alpha, int nq, const int *active, int nact);
 
 struct MGKernelBox {  // by-value kernel argument
   int n[3];
@@ -280,6 +294,7 @@ struct MGSolver {
   DevBuf norms;                    // [2*nq]: sum r^2, sum b^2 per plane
   std::vector<double> h_norms;
   bool use_tiles = false;
+  int plane_kernel = 0;            // 0: prefetch-ring kernels (mg_ring.cu), 1: shared-memory tiles, 2: register marching
   bool ids_local = false;          // neighbour ids of the solver boxes are solver-box indices (batched: blocks)
   bool plane_local = false;        // fused shared-memory path (planes not split over boxes)
   int first_smem_level = 0;        // first level handled by the one-CTA-per-plane kernel
@@ -287,6 +302,7 @@ struct MGSolver {
   int *d_active = nullptr, *d_where = nullptr, *d_iters = nullptr, *d_count = nullptr;  // per-plane stopping flags
   int *h_count = nullptr;          // pinned
   double last_mean_iters = 0.0;
+  int est_active = 0;              // planes still iterating at the last poll (sizes the work items of the next launches)
   void stats(Ctx &ctx, int *iters, double *relres, double *mean_iters);
   int last_iters = 0;
   double last_relres = 0.0;

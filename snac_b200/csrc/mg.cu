@@ -895,6 +895,13 @@ static void build_dir(MGLevelBox &L, int d, bool coupled, const std::vector<doub
     sam[i] = am[i] * srw[i]; sap[i] = ap[i] * srw[i]; se[i] = ad[i] * srw[i];
   }
   L.sam[d].upload(sam); L.sap[d].upload(sap); L.se[d].upload(se); L.srw[d].upload(srw);
+  std::vector<double> tab(8 * (size_t)(n + 2), 0.0);
+  for (int i = 0; i <= n + 1; ++i) {
+    double *t = &tab[8 * (size_t)i];
+    if (i >= 1 && i <= n) { t[0] = -sam[i]; t[1] = -sap[i]; t[2] = se[i]; t[3] = w[i]; t[4] = srw[i]; }
+    else t[2] = -1.0;   // outside cell: its update gives 0 and nothing couples to it
+  }
+  L.tab[d].upload(tab);
 }
 
 void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max_levels) {
@@ -1041,7 +1048,11 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
   }
   // ---- plane-local fast path -----------------------------------------------------------------
   plane_local = batched && !ctx.prm.mg_generic;
-  use_tiles = getenv("SNAC_MG_MARCH") == nullptr;   // A/B switch: SNAC_MG_MARCH selects the register-marching kernels
+  {  // A/B switch between the three implementations of the fused fine-level kernels
+    const char *k = getenv("SNAC_MG_KERNEL");
+    plane_kernel = !k ? 0 : (!strcmp(k, "tile") ? 1 : (!strcmp(k, "march") ? 2 : 0));
+    use_tiles = plane_kernel == 1;
+  }
   const int npre = ctx.prm.mg_npre > 0 ? ctx.prm.mg_npre : 1, npost = ctx.prm.mg_npost > 0 ? ctx.prm.mg_npost : 1;
   if (npre != 1 || npost != 1) plane_local = false;
   for (int lb = 0; lb < nl && plane_local; ++lb)
@@ -1178,6 +1189,16 @@ struct Cycle {
     P.per1 = S.sboxes[lb].nb[0][0] >= 0; P.per2 = S.sboxes[lb].nb[1][0] >= 0;
     return P;
   }
+  RLevel rlevel(int l, int lb) const {
+    const MGLevelBox &B = S.levels[l]->boxes[lb];
+    RLevel R;
+    R.n1 = B.g.n[0]; R.n2 = B.g.n[1];
+    R.sy = (int)B.g.sy; R.sz = B.g.sz;
+    R.ctab = B.tab[0].p(); R.rtab = B.tab[1].p();
+    R.c1 = S.levels[l]->coarsen[0]; R.c2 = S.levels[l]->coarsen[1];
+    R.per1 = S.sboxes[lb].nb[0][0] >= 0; R.per2 = S.sboxes[lb].nb[1][0] >= 0;
+    return R;
+  }
   double *xbuf(int l, int lb, int which) const {   // ping-pong buffers of the tiled levels
     return which == 0 ? S.levels[l]->boxes[lb].xp : S.x1[(size_t)l * S.levels[0]->boxes.size() + lb].p;
   }
@@ -1198,7 +1219,10 @@ struct Cycle {
       PLevel P = plevel(l, (int)lb);
       MGLevelBox &c = S.levels[l + 1]->boxes[lb];
       const double *xi = l == 0 ? xbuf(l, (int)lb, 0) : nullptr;   // below level 0 the iterate is zero on entry
-      if (S.use_tiles) {
+      if (S.plane_kernel == 0) {
+        launch_ring_down(ctx.stream, rlevel(l, (int)lb), xi, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy, c.g.sz, S.lam[lb].p(),
+                         S.alpha, norms ? S.norms.raw : nullptr, S.nq, want_b ? 1 : 0, S.d_active, S.est_active);
+      } else if (S.use_tiles) {
         dim3 grd((P.n1 + ptx(PH_D) - 1) / ptx(PH_D), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
         mg_plane_down_kernel<<<grd, 256, 0, ctx.stream>>>(P, xi, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy, c.g.sz,
                                                           S.lam[lb].p(), S.alpha, norms ? S.norms.raw : nullptr, S.nq, want_b ? 1 : 0, S.d_active);
@@ -1218,7 +1242,10 @@ struct Cycle {
     for (size_t lb = 0; lb < F.boxes.size(); ++lb) {
       PLevel P = plevel(l, (int)lb);
       MGLevelBox &c = S.levels[l + 1]->boxes[lb];
-      if (S.use_tiles) {
+      if (S.plane_kernel == 0) {
+        launch_ring_up(ctx.stream, rlevel(l, (int)lb), xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp, c.xp, c.g.sy, c.g.sz,
+                       S.lam[lb].p(), S.alpha, S.nq, S.d_active, S.est_active);
+      } else if (S.use_tiles) {
         dim3 grd((P.n1 + ptx(PH_U) - 1) / ptx(PH_U), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
         mg_plane_up_kernel<<<grd, 256, 0, ctx.stream>>>(P, xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp, c.xp, c.g.sy,
                                                         c.g.sz, S.lam[lb].p(), S.alpha, S.d_active);
@@ -1276,6 +1303,11 @@ void MGSolver::stats(Ctx &ctx, int *iters, double *relres, double *mean_iters) {
       last_mean_iters += it[q];
     }
     last_mean_iters /= nq;
+    if (getenv("SNAC_MG_DUMP")) {   // diagnostic: V-cycles per wavenumber
+      fprintf(stderr, "mg iters per plane:");
+      for (int q = 0; q < nq; ++q) fprintf(stderr, " %d", it[q]);
+      fprintf(stderr, "\n");
+    }
   }
   if (iters) *iters = last_iters;
   if (relres) *relres = last_relres;
@@ -1293,6 +1325,7 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
   mg_flags_init_kernel<<<1, 256, 0, ctx.stream>>>(S.d_active, S.d_where, S.d_iters, S.d_count, nq);
   ctx.launches++;
   int it = 0;
+  S.est_active = nq;
   for (;;) {
     const int batch = 3;
     for (int c = 0; c < batch; ++c, ++it) {
@@ -1313,6 +1346,7 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
     SNAC_CUDA(cudaMemcpyAsync(S.h_count, S.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
     SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
     if (*S.h_count == 0 || it > maxiter) break;
+    S.est_active = *S.h_count;
   }
   {
     ProfScope ps(ctx, PC_MG_COARSE);

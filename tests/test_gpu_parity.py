@@ -160,7 +160,11 @@ SOLVE_CASES = [("channel", 0, {}, False), ("channel", 1, {}, False), ("channel",
                ("channel", 2, dict(dims=(1, 1, 1), ng=(96, 8, 80)), False),
                ("channel", 2, dict(dims=(1, 1, 1), ng=(96, 8, 80)), True),
                ("channel", 1, dict(dims=(1, 1, 1), ng=(4, 200, 72)), False),
-               ("tgv", 2, dict(n=64), False)]
+               ("tgv", 2, dict(n=64), False),
+               # larger planes: strips with column halos, odd sizes, semi-coarsening on stretched walls
+               ("cavity", 2, dict(dims=(1, 1, 1), ng=(75, 6, 90)), False),
+               ("channel", 2, dict(dims=(1, 1, 1), ng=(160, 6, 130)), False),
+               ("tgv", 2, dict(n=128), False)]
 
 
 @pytest.mark.parametrize("kind,fa,kw,generic", SOLVE_CASES)
