@@ -246,9 +246,32 @@ struct RLevel {
   int per1, per2;            // periodic wrap onto the box itself
 };
 void launch_ring_down(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb, long csy,
-                      long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact);
+                      long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact, double xscale);
 void launch_ring_up(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, const double *cx, long csy,
                     long csz, const double *lamq, double alpha, int nq, const int *active, int nact);
+
+// every level from `ls` down in one shared-memory kernel, one CTA per plane (mg_coarse.cu)
+constexpr int CMAXLEV = 16;
+struct CoarseLevelArg {
+  int n1, n2, c1, c2, per1, per2;
+  const double *t1, *t2;     // packed coefficient tables of directions 0 and 1 (MGLevelBox::tab)
+};
+struct CoarseArgs {
+  CoarseLevelArg lev[CMAXLEV];
+  int nlev;
+  const double *b;           // right-hand side of the top level (ghosted layout, strides sy/sz)
+  const double *xin;         // incoming iterate of the top level, or nullptr (zero)
+  double *xout;
+  long sy, sz;
+  const double *lamq;
+  double alpha;
+  double *norms;             // only when the top level is level 0
+  double xscale;             // factor applied to xin
+  int nq, want_b, npre, npost, nbot;
+  const int *active;
+};
+size_t mg_coarse_smem(const CoarseArgs &a, bool single);
+void launch_mg_coarse(cudaStream_t st, const CoarseArgs &a, bool single);
 
 struct MGKernelBox {  // by-value kernel argument
   int n[3];
@@ -298,6 +321,8 @@ struct MGSolver {
   bool ids_local = false;          // neighbour ids of the solver boxes are solver-box indices (batched: blocks)
   bool plane_local = false;        // fused shared-memory path (planes not split over boxes)
   int first_smem_level = 0;        // first level handled by the one-CTA-per-plane kernel
+  bool coarse_single = false;      // that kernel computes in FP32 (only ever a coarse-grid correction, never level 0)
+  bool coarse_old = false;         // A/B switch: the previous shared-memory kernel
   std::vector<Field3> x1;          // second x buffer of the tiled levels [level*nbox + box]
   int *d_active = nullptr, *d_where = nullptr, *d_iters = nullptr, *d_count = nullptr;  // per-plane stopping flags
   int *h_count = nullptr;          // pinned
@@ -307,6 +332,7 @@ struct MGSolver {
   int last_iters = 0;
   double last_relres = 0.0;
   double alpha = 0.0;              // extra diagonal shift (IMPDIFF: alphai)
+  double guess_scale = 1.0;        // factor applied to the initial guess (the previous solution) by the first cycle
   void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched, int max_levels = 24);
   void solve(Ctx &ctx);
   const Grid3 &grid0(int lb) const { return levels[0]->boxes[lb].g; }
@@ -407,6 +433,7 @@ struct Ctx {
   std::vector<std::array<int, 3>> blocks_lo;
   std::vector<FFTRoute> route;              // per local box
   int par = 0;                              // which velocity buffer is current
+  double prev_dtrk = 0.0;                   // sub-step size of the previous pressure solve (initial-guess scaling)
   long long launches = 0;
   std::string err;
   // exchanges / BC fills

@@ -1062,26 +1062,41 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
         if (nb >= 0 && (ids_local ? nb : ctx.local_of_rank[nb]) != lb) plane_local = false;   // the plane is split over boxes
       }
   first_smem_level = 0;
-  // largest plane handed to the one-CTA-per-plane kernel (it is latency-bound: keep its top level small)
+  coarse_old = getenv("SNAC_MG_COARSE") && !strcmp(getenv("SNAC_MG_COARSE"), "old");
+  // largest plane handed to the previous one-CTA-per-plane kernel (it is latency-bound: keep its top level small)
   const size_t smem_cells = getenv("SNAC_MG_SMEM_CELLS") ? (size_t)atol(getenv("SNAC_MG_SMEM_CELLS")) : 2048;
   if (plane_local) {
     const int nlev = (int)levels.size();
-    // first level whose whole hierarchy below fits in shared memory (x and b per level)
+    // first level whose whole hierarchy below fits in shared memory (x and b per level): in FP64
+    // when that is level 0 (the kernel is then the whole solver), in FP32 below it (mg_coarse.cu)
     int ls = nlev - 1;
+    coarse_single = false;
     for (int l = nlev - 1; l >= 0; --l) {
       bool ok = true;
-      size_t worst = 0;
+      size_t worst = 0, tabs = 0;
       for (int lb = 0; lb < nl; ++lb) {
-        size_t c = 0;
-        for (int m = l; m < nlev; ++m) c += (size_t)levels[m]->boxes[lb].g.n[0] * levels[m]->boxes[lb].g.n[1];
+        size_t c = 0, t = 0;
+        for (int m = l; m < nlev; ++m) {
+          c += (size_t)levels[m]->boxes[lb].g.n[0] * levels[m]->boxes[lb].g.n[1];
+          t += (size_t)levels[m]->boxes[lb].g.n[0] + levels[m]->boxes[lb].g.n[1];
+        }
         worst = std::max(worst, c);
+        tabs = std::max(tabs, t);
       }
       size_t top = 0;
       for (int lb = 0; lb < nl; ++lb) top = std::max(top, (size_t)levels[l]->boxes[lb].g.n[0] * levels[l]->boxes[lb].g.n[1]);
-      if (nlev - l > PMAXLEV || worst * 2 * sizeof(double) > 160 * 1024 || (l < nlev - 1 && top > smem_cells)) ok = false;
+      if (coarse_old) {
+        if (nlev - l > PMAXLEV || worst * 2 * sizeof(double) > 160 * 1024 || (l < nlev - 1 && top > smem_cells)) ok = false;
+      } else {
+        const size_t elems = 2 * worst + 5 * tabs;
+        const size_t bytes = elems * (l == 0 ? sizeof(double) : sizeof(float));
+        if (nlev - l > CMAXLEV || bytes > 200 * 1024) ok = false;
+        if (getenv("SNAC_MG_SMEM_CELLS") && l < nlev - 1 && top > smem_cells) ok = false;   // test hook: force the streaming kernels
+      }
       if (!ok) break;
       ls = l;
     }
+    coarse_single = !coarse_old && ls > 0;
     first_smem_level = ls;
     // the tiled kernels need an even size in every periodic direction of the levels they handle
     for (int l = 0; l < ls && plane_local; ++l)
@@ -1221,7 +1236,7 @@ struct Cycle {
       const double *xi = l == 0 ? xbuf(l, (int)lb, 0) : nullptr;   // below level 0 the iterate is zero on entry
       if (S.plane_kernel == 0) {
         launch_ring_down(ctx.stream, rlevel(l, (int)lb), xi, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy, c.g.sz, S.lam[lb].p(),
-                         S.alpha, norms ? S.norms.raw : nullptr, S.nq, want_b ? 1 : 0, S.d_active, S.est_active);
+                         S.alpha, norms ? S.norms.raw : nullptr, S.nq, want_b ? 1 : 0, S.d_active, S.est_active, (l == 0 && want_b) ? S.guess_scale : 1.0);
       } else if (S.use_tiles) {
         dim3 grd((P.n1 + ptx(PH_D) - 1) / ptx(PH_D), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
         mg_plane_down_kernel<<<grd, 256, 0, ctx.stream>>>(P, xi, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy, c.g.sz,
@@ -1261,7 +1276,33 @@ struct Cycle {
   void plane_coarse(bool norms, bool want_b) {
     const int ls = S.first_smem_level, nlev = (int)S.levels.size();
     ProfScope ps(ctx, ls == 0 ? PC_MG_DOWN0 : PC_MG_COARSE);
-    for (size_t lb = 0; lb < S.levels[ls]->boxes.size(); ++lb) {
+    for (size_t lb = 0; lb < S.levels[ls]->boxes.size() && !S.coarse_old; ++lb) {
+      CoarseArgs a;
+      a.nlev = nlev - ls;
+      for (int l = ls; l < nlev; ++l) {
+        const MGLevelBox &B = S.levels[l]->boxes[lb];
+        CoarseLevelArg &c = a.lev[l - ls];
+        c.n1 = B.g.n[0]; c.n2 = B.g.n[1];
+        c.c1 = S.levels[l]->coarsen[0]; c.c2 = S.levels[l]->coarsen[1];
+        c.per1 = S.sboxes[lb].nb[0][0] >= 0; c.per2 = S.sboxes[lb].nb[1][0] >= 0;
+        c.t1 = B.tab[0].p(); c.t2 = B.tab[1].p();
+      }
+      MGLevelBox &T = S.levels[ls]->boxes[lb];
+      a.b = T.bp;
+      a.xin = ls == 0 ? T.xp : nullptr;
+      a.xout = T.xp;
+      a.sy = T.g.sy; a.sz = T.g.sz;
+      a.lamq = S.lam[lb].p();
+      a.alpha = S.alpha;
+      a.norms = (ls == 0 && norms) ? S.norms.raw : nullptr;
+      a.xscale = (ls == 0 && want_b) ? S.guess_scale : 1.0;
+      a.nq = S.nq; a.want_b = want_b ? 1 : 0;
+      a.npre = npre; a.npost = npost; a.nbot = nbot;
+      a.active = S.d_active;
+      launch_mg_coarse(ctx.stream, a, S.coarse_single);
+      ctx.launches++;
+    }
+    for (size_t lb = 0; lb < S.levels[ls]->boxes.size() && S.coarse_old; ++lb) {
       PCoarseArgs a;
       a.nlev = nlev - ls;
       size_t cells = 0;

@@ -1,0 +1,327 @@
+// K4, plane-local fast path: every level of a V-cycle from level `ls` down in ONE kernel, one CTA
+// per wavenumber plane, all iterates and right-hand sides of those levels resident in shared
+// memory (see mg.cu for the operator, the cycle and the reference call sites,
+// src/solver.f90:843-922).
+//
+// When the kernel starts at level 0 (planes small enough to fit) it is the whole solver cycle and
+// works in FP64.  When it starts below level 0 it only produces the coarse-grid correction of the
+// FP64 fine-level kernels (mg_ring.cu): that correction is computed in FP32 -- an error of 1e-7
+// relative to a correction that itself only has to reduce the fine residual by a factor of ~4 per
+// cycle does not change the convergence, the fine-level residual and the iterate stay FP64 -- which
+// halves the shared-memory footprint, so that twice as large a level (e.g. 128 x 128 for 256 x 256
+// planes) can be taken off the HBM-streaming kernels.
+//
+// Equations are used in the scaled form (division by w1*w2, as in mg_ring.cu):
+//   x = ( b~ + na1m xL + na1p xR + na2m xD + na2p xU ) / (e1 + e2 + lambda)
+// and the restriction of the (unscaled) residual by summation over the children becomes
+//   b~_c(I,J) = sum_children (w1_i / W1_I)(w2_j / W2_J) r~(i,j),   W = width of the coarse cell.
+#include "common.h"
+
+namespace snac {
+
+namespace {
+
+struct CLev {      // one level as laid out in shared memory (offsets in elements from the base)
+  int n1, n2, c1, c2, per1, per2;
+  int ox, ob;      // x, b: [n2][n1]
+  int o1, o2;      // tables of directions 0/1: [5][n]: na_m, na_p, e, restriction weight w/W, w
+};
+
+__device__ __forceinline__ double c_rcp(double e) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(e));
+  double t = fma(-e, r, 1.0);
+  r = fma(r, t, r);
+  t = fma(-e, r, 1.0);
+  return fma(r, t, r);
+}
+__device__ __forceinline__ float c_rcp(float e) {   // 1 ulp is plenty for a coarse-grid smoother
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e));
+  return r;
+}
+
+// A phase is executed by a group of nthr threads (the whole CTA, or warp 0 alone on the smallest
+// levels, where a block-wide barrier per phase would cost more than the work).  2-D thread layout
+// of a level inside the group: W = 2^lw threads along direction 0, the rest along direction 1.
+struct CGroup {
+  int tid, nthr;   // nthr is a power of two
+  bool warp;       // the group is one warp: phases are separated by __syncwarp
+  __device__ __forceinline__ void sync() const {
+    if (warp) __syncwarp();
+    else __syncthreads();
+  }
+  __device__ __forceinline__ int lw(int n) const {
+    const int m = min(max(n, 1), nthr);
+    return 32 - __clz(m - 1);   // ceil(log2(m))
+  }
+};
+
+// residual of the scaled equation at cell (i, j)
+template <class T>
+__device__ __forceinline__ T c_resid(const T *sm, const CLev &L, int i, int j, T lam) {
+  const int n1 = L.n1, n2 = L.n2;
+  const int im = i > 0 ? i - 1 : (L.per1 ? n1 - 1 : 0), ip = i < n1 - 1 ? i + 1 : (L.per1 ? 0 : n1 - 1);
+  const int jm = j > 0 ? j - 1 : (L.per2 ? n2 - 1 : 0), jp = j < n2 - 1 ? j + 1 : (L.per2 ? 0 : n2 - 1);
+  const T *x = sm + L.ox, *t1 = sm + L.o1, *t2 = sm + L.o2;
+  const T e = t1[2 * n1 + i] + t2[2 * n2 + j] + lam;
+  T acc = sm[L.ob + j * n1 + i];
+  acc = fma(t1[i], x[j * n1 + im], acc);
+  acc = fma(t1[n1 + i], x[j * n1 + ip], acc);
+  acc = fma(t2[j], x[jm * n1 + i], acc);
+  acc = fma(t2[n2 + j], x[jp * n1 + i], acc);
+  return fma(-e, x[j * n1 + i], acc);
+}
+
+// one colour of a Gauss-Seidel sweep: a thread keeps its column and walks over rows of one parity
+template <class T>
+__device__ __forceinline__ void c_sweep(T *sm, const CLev &L, int color, T lam, const CGroup &G) {
+  const int n1 = L.n1, n2 = L.n2, h1 = (n1 + 1) >> 1, per1 = L.per1, per2 = L.per2;
+  const int lw = G.lw(h1), W = 1 << lw, tx = G.tid & (W - 1), ty = G.tid >> lw, nty = G.nthr >> lw;
+  T *x = sm + L.ox;
+  const T *b = sm + L.ob, *t1 = sm + L.o1, *t2 = sm + L.o2;
+  if (G.tid < G.nthr) {
+    // rows j = ty, ty + nty, ...: all of one parity when nty is even, so the column is fixed;
+    // with a single row of threads (nty == 1) walk the two parities one after the other
+    const int npar = (nty & 1) ? 2 : 1, jstep = (nty & 1) ? 2 * nty : nty;
+    const int wlo = per2 ? (n2 - 1) * n1 : 0, whi = per2 ? -(n2 - 1) * n1 : 0;   // row offsets of the wrapped / clamped neighbours
+    for (int p = tx; p < h1; p += W) {
+      for (int par = 0; par < npar; ++par) {
+        const int jfirst = ty + par * nty;
+        const int i = 2 * p + ((color + jfirst) & 1);
+        if (i >= n1) continue;
+        const int im = i > 0 ? i - 1 : (per1 ? n1 - 1 : 0), ip = i < n1 - 1 ? i + 1 : (per1 ? 0 : n1 - 1);
+        const T cm = t1[i], cp = t1[n1 + i], e1 = t1[2 * n1 + i] + lam;
+        T *xc = x + i;
+        const T *xl = x + im, *xr = x + ip, *bc = b + i;
+#pragma unroll 2
+        for (int j = jfirst; j < n2; j += jstep) {
+          const int o = j * n1;
+          const int om = j > 0 ? o - n1 : o + wlo, op = j < n2 - 1 ? o + n1 : o + whi;
+          const T e = e1 + t2[2 * n2 + j];
+          T acc = bc[o];
+          T acc2 = t2[j] * xc[om];
+          acc = fma(cm, xl[o], acc);
+          acc2 = fma(t2[n2 + j], xc[op], acc2);
+          acc = fma(cp, xr[o], acc);
+          // e == 0: a singular one-cell level, nothing to solve (the update would be 0/0)
+          xc[o] = e != (T)0 ? (acc + acc2) * c_rcp(e) : xc[o];
+        }
+      }
+    }
+  }
+  G.sync();
+}
+
+// pre-relaxation on level F, residual restricted to level C (whose iterate is zeroed)
+template <class T>
+__device__ __forceinline__ void c_down(T *sm, const CLev &F, const CLev &C, T lam, int npre, const CGroup &G, bool want_norm,
+                                       double &r2, double &b2) {
+  for (int s = 0; s < npre; ++s) { c_sweep(sm, F, 0, lam, G); c_sweep(sm, F, 1, lam, G); }
+  const T *f1 = sm + F.o1, *f2 = sm + F.o2;
+  const int lw = G.lw(C.n1), W = 1 << lw, tx = G.tid & (W - 1), ty = G.tid >> lw, nty = G.nthr >> lw;
+  if (G.tid < G.nthr) {
+    for (int I = tx; I < C.n1; I += W) {
+      const int i0 = F.c1 ? 2 * I : I, i1 = F.c1 ? min(2 * I + 1, F.n1 - 1) : I;
+      for (int J = ty; J < C.n2; J += nty) {
+        const int j0 = F.c2 ? 2 * J : J, j1 = F.c2 ? min(2 * J + 1, F.n2 - 1) : J;
+        T sum = (T)0;
+        for (int j = j0; j <= j1; ++j)
+          for (int i = i0; i <= i1; ++i) {
+            if (want_norm) {
+              const double bb = (double)sm[F.ob + j * F.n1 + i] * ((double)f1[4 * F.n1 + i] * (double)f2[4 * F.n2 + j]);
+              b2 += bb * bb;
+            }
+            if ((i + j) & 1) continue;   // after the second colour its own residual vanishes
+            const T r = c_resid(sm, F, i, j, lam);
+            sum = fma(f1[3 * F.n1 + i] * f2[3 * F.n2 + j], r, sum);
+            if (want_norm) {
+              const double rr = (double)r * ((double)f1[4 * F.n1 + i] * (double)f2[4 * F.n2 + j]);
+              r2 += rr * rr;
+            }
+          }
+        sm[C.ob + J * C.n1 + I] = sum;
+        sm[C.ox + J * C.n1 + I] = (T)0;
+      }
+    }
+  }
+  G.sync();
+}
+
+// correction from level C added to level F, post-relaxation
+template <class T>
+__device__ __forceinline__ void c_up(T *sm, const CLev &F, const CLev &C, T lam, int npost, const CGroup &G) {
+  const int lw = G.lw(F.n1), W = 1 << lw, tx = G.tid & (W - 1), ty = G.tid >> lw, nty = G.nthr >> lw;
+  if (G.tid < G.nthr) {
+    for (int i = tx; i < F.n1; i += W) {
+      const int I = F.c1 ? i >> 1 : i;
+#pragma unroll 4
+      for (int j = ty; j < F.n2; j += nty) sm[F.ox + j * F.n1 + i] += sm[C.ox + (F.c2 ? j >> 1 : j) * C.n1 + I];
+    }
+  }
+  G.sync();
+  for (int s = 0; s < npost; ++s) { c_sweep(sm, F, 1, lam, G); c_sweep(sm, F, 0, lam, G); }
+}
+
+}  // namespace
+
+template <class T>
+__global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ CLev lv[CMAXLEV];
+  __shared__ double red[2][32];
+  T *sm = reinterpret_cast<T *>(smem_raw);
+  const int q = blockIdx.x;
+  if (a.active && !a.active[q]) return;
+  const T lam = (T)(a.alpha + __ldg(a.lamq + q + 1));
+  const int nlev = a.nlev;
+  const CGroup GB{(int)threadIdx.x, (int)blockDim.x, false}, GW{(int)threadIdx.x, 32, true};
+  if (threadIdx.x == 0) {   // carve the shared memory
+    int p = 0;
+    for (int l = 0; l < nlev; ++l) {
+      CLev &L = lv[l];
+      L.n1 = a.lev[l].n1; L.n2 = a.lev[l].n2;
+      L.c1 = a.lev[l].c1; L.c2 = a.lev[l].c2; L.per1 = a.lev[l].per1; L.per2 = a.lev[l].per2;
+      L.ox = p; p += L.n1 * L.n2;
+      L.ob = p; p += L.n1 * L.n2;
+      L.o1 = p; p += 5 * L.n1;
+      L.o2 = p; p += 5 * L.n2;
+    }
+  }
+  __syncthreads();
+  // first level left to warp 0 alone (at most 256 cells); level 0 always belongs to the CTA
+  int lsw = nlev;
+  while (lsw > 1 && lv[lsw - 1].n1 * lv[lsw - 1].n2 <= 256) --lsw;
+  // coefficient tables (global tables are 1-based with 8 doubles per entry: na_m, na_p, e, w, 1/w)
+  for (int l = 0; l < nlev; ++l) {
+    const CLev L = lv[l];
+    for (int d = 0; d < 2; ++d) {
+      const int n = d ? L.n2 : L.n1;
+      const int co = d ? L.c2 : L.c1;
+      const double *g = d ? a.lev[l].t2 : a.lev[l].t1;
+      const double *gc = l + 1 < nlev ? (d ? a.lev[l + 1].t2 : a.lev[l + 1].t1) : nullptr;
+      T *t = sm + (d ? L.o2 : L.o1);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double *e = g + 8 * (i + 1);
+        t[i] = (T)__ldg(e); t[n + i] = (T)__ldg(e + 1); t[2 * n + i] = (T)__ldg(e + 2);
+        const double w = __ldg(e + 3);
+        t[4 * n + i] = (T)w;
+        t[3 * n + i] = (gc && co) ? (T)(w / __ldg(gc + 8 * ((i >> 1) + 1) + 3)) : (T)1;
+      }
+    }
+  }
+  // top level: right-hand side (scaled) and iterate; rows of the plane are contiguous in memory
+  {
+    const CLev L = lv[0];
+    const long qoff = (long)(q + 1) * a.sz;
+    const int n1 = L.n1, n2 = L.n2;
+    const int lw = GB.lw(n1), W = 1 << lw, tx = threadIdx.x & (W - 1), ty = threadIdx.x >> lw, nty = blockDim.x >> lw;
+    for (int i = tx; i < n1; i += W) {
+      const double s1 = __ldg(a.lev[0].t1 + 8 * (i + 1) + 4);
+#pragma unroll 8
+      for (int j = ty; j < n2; j += nty) {
+        const long o = qoff + (i + 1) + a.sy * (j + 1);
+        const double s = s1 * __ldg(a.lev[0].t2 + 8 * (j + 1) + 4);
+        sm[L.ob + j * n1 + i] = (T)(__ldg(a.b + o) * s);
+        sm[L.ox + j * n1 + i] = a.xin ? (T)(a.xin[o] * a.xscale) : (T)0;
+      }
+    }
+  }
+  __syncthreads();
+  double r2 = 0.0, b2 = 0.0;
+  // ---- down leg, CTA-wide levels
+  for (int l = 0; l < lsw - 1; ++l) {
+    const CLev F = lv[l], C = lv[l + 1];
+    c_down(sm, F, C, lam, a.npre, GB, l == 0 && a.norms, r2, b2);
+  }
+  // ---- from level lsw-1 down: restriction into the first small level by the CTA, then warp 0 runs
+  //      the rest of the cycle on the small levels by itself
+  if (lsw < nlev) {
+    {
+      const CLev F = lv[lsw - 1], C = lv[lsw];
+      c_down(sm, F, C, lam, a.npre, GB, lsw == 1 && a.norms, r2, b2);
+    }
+    if (threadIdx.x < 32) {
+      for (int l = lsw; l < nlev - 1; ++l) {
+        const CLev F = lv[l], C = lv[l + 1];
+        c_down(sm, F, C, lam, a.npre, GW, false, r2, b2);
+      }
+      const CLev B = lv[nlev - 1];
+      const int ns = min(a.nbot, B.n1 * B.n2);   // a 1 x 1 level is solved by one update
+      for (int s = 0; s < ns; ++s) { c_sweep(sm, B, 0, lam, GW); c_sweep(sm, B, 1, lam, GW); }
+      for (int l = nlev - 2; l >= lsw; --l) {
+        const CLev F = lv[l], C = lv[l + 1];
+        c_up(sm, F, C, lam, a.npost, GW);
+      }
+    }
+    __syncthreads();
+    {
+      const CLev F = lv[lsw - 1], C = lv[lsw];
+      c_up(sm, F, C, lam, a.npost, GB);
+    }
+  } else {   // the coarsest level belongs to the CTA (a single-level or all-large hierarchy)
+    const CLev B = lv[nlev - 1];
+    const int ns = min(a.nbot, B.n1 * B.n2);
+    for (int s = 0; s < ns; ++s) { c_sweep(sm, B, 0, lam, GB); c_sweep(sm, B, 1, lam, GB); }
+    if (nlev == 1 && a.norms) {
+      for (int t = threadIdx.x; t < B.n1 * B.n2; t += blockDim.x) {
+        const int j = t / B.n1, i = t - j * B.n1;
+        const double w = (double)sm[B.o1 + 4 * B.n1 + i] * (double)sm[B.o2 + 4 * B.n2 + j];
+        const double rr = (double)c_resid(sm, B, i, j, lam) * w, bb = (double)sm[B.ob + t] * w;
+        r2 += rr * rr;
+        b2 += bb * bb;
+      }
+    }
+  }
+  // ---- up leg, CTA-wide levels
+  for (int l = lsw - 2; l >= 0; --l) {
+    const CLev F = lv[l], C = lv[l + 1];
+    c_up(sm, F, C, lam, a.npost, GB);
+  }
+  // ---- result
+  {
+    const CLev L = lv[0];
+    const long qoff = (long)(q + 1) * a.sz;
+    const int n1 = L.n1, n2 = L.n2;
+    const int lw = GB.lw(n1), W = 1 << lw, tx = threadIdx.x & (W - 1), ty = threadIdx.x >> lw, nty = blockDim.x >> lw;
+    for (int i = tx; i < n1; i += W)
+#pragma unroll 4
+      for (int j = ty; j < n2; j += nty) a.xout[qoff + (i + 1) + a.sy * (j + 1)] = (double)sm[L.ox + j * n1 + i];
+  }
+  if (a.norms) {
+    for (int o = 16; o > 0; o >>= 1) {
+      r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = r2; red[1][threadIdx.x >> 5] = b2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { r2 += red[0][w]; b2 += red[1][w]; }
+      atomicAdd(a.norms + q, r2);
+      if (a.want_b) atomicAdd(a.norms + a.nq + q, b2);
+    }
+  }
+}
+
+size_t mg_coarse_smem(const CoarseArgs &a, bool single) {
+  size_t elems = 0;
+  for (int l = 0; l < a.nlev; ++l) elems += 2 * (size_t)a.lev[l].n1 * a.lev[l].n2 + 5 * (size_t)(a.lev[l].n1 + a.lev[l].n2);
+  return elems * (single ? sizeof(float) : sizeof(double)) + 16;
+}
+
+void launch_mg_coarse(cudaStream_t st, const CoarseArgs &a, bool single) {
+  const size_t smem = mg_coarse_smem(a, single);
+  const long top = (long)a.lev[0].n1 * a.lev[0].n2;
+  int nt = 128;
+  while (nt < 1024 && nt * 8 < top) nt *= 2;   // about eight cells of the top level per thread
+  static size_t cap[2] = {48 * 1024, 48 * 1024};
+  if (smem > cap[single]) {
+    if (single) SNAC_CUDA(cudaFuncSetAttribute(mg_coarse_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else SNAC_CUDA(cudaFuncSetAttribute(mg_coarse_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cap[single] = smem;
+  }
+  if (single) mg_coarse_kernel<float><<<a.nq, nt, smem, st>>>(a);
+  else mg_coarse_kernel<double><<<a.nq, nt, smem, st>>>(a);
+}
+
+}  // namespace snac

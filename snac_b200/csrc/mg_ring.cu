@@ -134,7 +134,7 @@ struct Down {
   const double *xsrc, *bsrc;
   double *xdst, *cbq;
   int csy, lane, j0, mry, HT, want_b;
-  double wc0, wc1;
+  double wc0, wc1, xscale;   // xscale: factor applied to the incoming iterate (initial guess)
   double xa[RD], xb[RD];   // register window (indexed by row mod RD; only about seven rows are live at a time)
   double r2 = 0.0, b2 = 0.0, resP = 0.0;
 
@@ -168,7 +168,7 @@ struct Down {
       const double *slot = ring + S * SLOT_D;
       if (HASX) {
         const double2 v = *reinterpret_cast<const double2 *>(slot + 2 * lane);
-        xa[S] = v.x; xb[S] = v.y;
+        xa[S] = v.x * xscale; xb[S] = v.y * xscale;
       } else {
         xa[S] = 0.0; xb[S] = 0.0;
       }
@@ -313,7 +313,7 @@ template <bool WRAP, bool HASX, int CM>
 __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel L, const double *__restrict__ xin, double *__restrict__ xout,
                                                                     const double *__restrict__ b, double *__restrict__ cb, int csy, long csz,
                                                                     const double *lamq, double alpha, double *norms, int nq, int want_b,
-                                                                    int ntx, int nty, int mry, const int *active) {
+                                                                    int ntx, int nty, int mry, const int *active, double xscale) {
   using D = Down<WRAP, HASX, CM>;
   extern __shared__ __align__(16) double ring_all[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel
   s.HT = mry + 2 * D::HY;
   s.want_b = want_b;
   s.csy = csy;
+  s.xscale = xscale;
   const long qoff = (long)(q + 1) * L.sz;
   ring_cols<D::HX, WRAP>(L, 1 + tx * D::TX, alpha + __ldg(lamq + q + 1), lane, s.C);
   s.ring = ring_all + (size_t)wib * RD * SLOT_D;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel
     __syncwarp();
     if (HASX) {
       const double2 v = *reinterpret_cast<const double2 *>(s.ring + 2 * lane);
-      s.xa[0] = v.x; s.xb[0] = v.y;
+      s.xa[0] = v.x * xscale; s.xb[0] = v.y * xscale;
     }
   }
   for (int t0 = 0; t0 < s.HT + 1; t0 += RD) {   // the last kept row leaves at step HT + 1 - 1
@@ -459,24 +460,24 @@ static void ring_smem(K kernel, size_t bytes) {
 template <bool WRAP, bool HASX, int CM>
 static void ring_down_go(unsigned grid, cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb,
                          int csy, long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, int ntx, int nty,
-                         int mry, const int *active) {
+                         int mry, const int *active, double xscale) {
   constexpr size_t smem = (size_t)WARPS_D * RD * SLOT_D * sizeof(double);
   ring_smem<WRAP * 8 + HASX * 4 + CM>(mg_ring_down_kernel<WRAP, HASX, CM>, smem);
   mg_ring_down_kernel<WRAP, HASX, CM><<<grid, WARPS_D * 32, smem, st>>>(L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx,
-                                                                        nty, mry, active);
+                                                                        nty, mry, active, xscale);
 }
 
 template <bool WRAP, bool HASX>
 static void ring_down_cm(int cm, unsigned grid, cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b,
                          double *cb, int csy, long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, int ntx,
-                         int nty, int mry, const int *active) {
-  if (cm == CM_FULL) ring_down_go<WRAP, HASX, CM_FULL>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active);
-  else if (cm == CM_X) ring_down_go<WRAP, HASX, CM_X>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active);
-  else ring_down_go<WRAP, HASX, CM_Y>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active);
+                         int nty, int mry, const int *active, double xscale) {
+  if (cm == CM_FULL) ring_down_go<WRAP, HASX, CM_FULL>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
+  else if (cm == CM_X) ring_down_go<WRAP, HASX, CM_X>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
+  else ring_down_go<WRAP, HASX, CM_Y>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
 }
 
 void launch_ring_down(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb, long csy,
-                      long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact) {
+                      long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact, double xscale) {
   const bool wrap = L.per1 && L.n1 == RW;
   const int tx = wrap ? RW : RW - 8;
   const int mry = ring_rows(L.n1, L.n2, nact, tx, 3, 2, RD);   // HT + 2 steps
@@ -485,11 +486,11 @@ void launch_ring_down(cudaStream_t st, const RLevel &L, const double *xin, doubl
   const unsigned grid = (unsigned)((nw + WARPS_D - 1) / WARPS_D);
   const int cm = (L.c1 && L.c2) ? CM_FULL : (L.c1 ? CM_X : CM_Y);
   if (wrap) {
-    if (xin) ring_down_cm<true, true>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active);
-    else ring_down_cm<true, false>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active);
+    if (xin) ring_down_cm<true, true>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
+    else ring_down_cm<true, false>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
   } else {
-    if (xin) ring_down_cm<false, true>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active);
-    else ring_down_cm<false, false>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active);
+    if (xin) ring_down_cm<false, true>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
+    else ring_down_cm<false, false>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
   }
 }
 

@@ -171,6 +171,23 @@ SOLVE_CASES = [("channel", 0, {}, False), ("channel", 1, {}, False), ("channel",
 def test_solver_against_exact_solution(tmp_path, kind, fa, kw, generic):
     """multigrid solution of the reference's linear system vs. the sparse-direct solution of the
     same system (oracle LinearSystem), tolerance 1e-11 on the relative residual."""
+    _solve_and_compare(tmp_path, kind, fa, kw, generic)
+
+
+# planes that would fit the one-kernel-per-plane path, forced through the HBM-streaming fine-level
+# kernels + FP32 shared-memory coarse kernel instead (the path large planes take)
+STREAM_CASES = [("channel", 2, dict(dims=(1, 1, 1), ng=(96, 8, 80))), ("channel", 1, dict(dims=(1, 1, 1), ng=(4, 200, 72))),
+                ("tgv", 2, dict(n=64)), ("tgv", 1, dict(n=32)), ("channel", 2, dict(dims=(1, 1, 1), ng=(64, 4, 66)))]
+
+
+@pytest.mark.parametrize("kind,fa,kw", STREAM_CASES)
+@pytest.mark.parametrize("cells", [300, 1500])
+def test_solver_streaming_kernels(tmp_path, monkeypatch, kind, fa, kw, cells):
+    monkeypatch.setenv("SNAC_MG_SMEM_CELLS", str(cells))
+    _solve_and_compare(tmp_path, kind, fa, kw, False)
+
+
+def _solve_and_compare(tmp_path, kind, fa, kw, generic):
     case = cases.make(kind, str(tmp_path), fft_axis=fa, **kw)
     fields = cases.random_fields(case, seed=7)
     o, g = make_pair(case, fields, tol=1e-11, maxiter=200, mg_generic=generic)
