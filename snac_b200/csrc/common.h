@@ -245,9 +245,9 @@ struct RLevel {
   int c1, c2;                // directions coarsened towards the next level
   int per1, per2;            // periodic wrap onto the box itself
 };
-void launch_ring_down(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb, long csy,
+void launch_ring_down(cudaStream_t st, const RLevel &L, int nsweep, const double *xin, double *xout, const double *b, double *cb, long csy,
                       long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact, double xscale);
-void launch_ring_up(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, const double *cx, long csy,
+void launch_ring_up(cudaStream_t st, const RLevel &L, int nsweep, const double *xin, double *xout, const double *b, const double *cx, long csy,
                     long csz, const double *lamq, double alpha, int nq, const int *active, int nact);
 
 // every level from `ls` down in one shared-memory kernel, one CTA per plane (mg_coarse.cu)
@@ -332,6 +332,8 @@ struct MGSolver {
   int last_iters = 0;
   double last_relres = 0.0;
   double alpha = 0.0;              // extra diagonal shift (IMPDIFF: alphai)
+  int default_sweeps = 2;          // smoothing sweeps per leg when snac_params does not say: V(2,2) converges at ~0.13 per
+                                   // cycle on isotropic grids (V(1,1): 0.27) and stays convergent on stretched / anisotropic ones
   double guess_scale = 1.0;        // factor applied to the initial guess (the previous solution) by the first cycle
   void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched, int max_levels = 24);
   void solve(Ctx &ctx);

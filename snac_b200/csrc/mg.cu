@@ -843,6 +843,14 @@ __global__ void mg_finalize_kernel(double *x0, const double *x1, long sy, long s
 // ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
+// smoothing sweeps per leg of the V-cycle: snac_params, else SNAC_MG_NSWEEP, else the solver's default
+static void mg_sweeps(const Ctx &ctx, const MGSolver &S, int &npre, int &npost) {
+  int def = S.default_sweeps;
+  if (const char *e = getenv("SNAC_MG_NSWEEP")) def = std::max(1, atoi(e));
+  npre = ctx.prm.mg_npre > 0 ? ctx.prm.mg_npre : def;
+  npost = ctx.prm.mg_npost > 0 ? ctx.prm.mg_npost : def;
+}
+
 static dim3 mg_block(const Grid3 &g, int fft_dir) {
   // threads of a block must share the plane index along z when that is the batch direction
   dim3 b;
@@ -1053,8 +1061,10 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
     plane_kernel = !k ? 0 : (!strcmp(k, "tile") ? 1 : (!strcmp(k, "march") ? 2 : 0));
     use_tiles = plane_kernel == 1;
   }
-  const int npre = ctx.prm.mg_npre > 0 ? ctx.prm.mg_npre : 1, npost = ctx.prm.mg_npost > 0 ? ctx.prm.mg_npost : 1;
-  if (npre != 1 || npost != 1) plane_local = false;
+  int npre, npost;
+  mg_sweeps(ctx, *this, npre, npost);
+  if (npre != npost || npre > 2) plane_local = false;
+  if (npre == 2 && plane_kernel != 0) plane_local = false;   // only the prefetch-ring kernels do two sweeps per leg
   for (int lb = 0; lb < nl && plane_local; ++lb)
     for (int d = 0; d < 2; ++d)
       for (int ib = 0; ib < 2; ++ib) {
@@ -1235,7 +1245,7 @@ struct Cycle {
       MGLevelBox &c = S.levels[l + 1]->boxes[lb];
       const double *xi = l == 0 ? xbuf(l, (int)lb, 0) : nullptr;   // below level 0 the iterate is zero on entry
       if (S.plane_kernel == 0) {
-        launch_ring_down(ctx.stream, rlevel(l, (int)lb), xi, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy, c.g.sz, S.lam[lb].p(),
+        launch_ring_down(ctx.stream, rlevel(l, (int)lb), npre, xi, xbuf(l, (int)lb, 1), F.boxes[lb].bp, c.bp, c.g.sy, c.g.sz, S.lam[lb].p(),
                          S.alpha, norms ? S.norms.raw : nullptr, S.nq, want_b ? 1 : 0, S.d_active, S.est_active, (l == 0 && want_b) ? S.guess_scale : 1.0);
       } else if (S.use_tiles) {
         dim3 grd((P.n1 + ptx(PH_D) - 1) / ptx(PH_D), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
@@ -1258,7 +1268,7 @@ struct Cycle {
       PLevel P = plevel(l, (int)lb);
       MGLevelBox &c = S.levels[l + 1]->boxes[lb];
       if (S.plane_kernel == 0) {
-        launch_ring_up(ctx.stream, rlevel(l, (int)lb), xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp, c.xp, c.g.sy, c.g.sz,
+        launch_ring_up(ctx.stream, rlevel(l, (int)lb), npost, xbuf(l, (int)lb, 1), xbuf(l, (int)lb, 0), F.boxes[lb].bp, c.xp, c.g.sy, c.g.sz,
                        S.lam[lb].p(), S.alpha, S.nq, S.d_active, S.est_active);
       } else if (S.use_tiles) {
         dim3 grd((P.n1 + ptx(PH_U) - 1) / ptx(PH_U), (P.n2 + PT_Y - 1) / PT_Y, S.nq);
@@ -1403,8 +1413,9 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
 }
 
 void MGSolver::solve(Ctx &ctx) {
-  Cycle cy{ctx, *this, {fft_dir != 0, fft_dir != 1, fft_dir != 2},
-           ctx.prm.mg_npre > 0 ? ctx.prm.mg_npre : 1, ctx.prm.mg_npost > 0 ? ctx.prm.mg_npost : 1,
+  int npre, npost;
+  mg_sweeps(ctx, *this, npre, npost);
+  Cycle cy{ctx, *this, {fft_dir != 0, fft_dir != 1, fft_dir != 2}, npre, npost,
            ctx.prm.mg_nbottom > 0 ? ctx.prm.mg_nbottom : 20};
   if (plane_local) {
     solve_plane_local(ctx, *this, cy);

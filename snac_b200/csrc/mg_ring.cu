@@ -38,7 +38,7 @@ namespace {
 constexpr int RW = 64;    // columns per warp
 constexpr int RD = 12;    // ring slots = window slots = unroll period of the march, down kernel
 constexpr int RDU = 8;    // the same for the up kernel (rows leave the window earlier there)
-constexpr int RP_D = 6, RP_U = 5;   // rows in flight ahead of the one entering the window (a slot must outlive the last use of its row)
+constexpr int RP_D = 6;   // rows in flight ahead of the one entering the window (a slot must outlive the last use of its row)
 constexpr int WARPS_D = 4, WARPS_U = 2;   // warps per CTA (independent of each other)
 constexpr int SLOT_D = 64 + 64 + 8;       // doubles per ring slot, down: x, b, coefficients
 constexpr int SLOT_U = 64 + 64 + 64 + 8;  // up: x, b, coarse x, coefficients
@@ -123,9 +123,17 @@ __device__ __forceinline__ double ring_upd(bool A, const ColPair &C, const doubl
 constexpr int CM_FULL = 0, CM_X = 1, CM_Y = 2;   // directions coarsened towards the next level
 
 // ---- down ------------------------------------------------------------------------------------
-template <bool WRAP, bool HASX, int CM>
+// NSW Gauss-Seidel sweeps (colour 0 then 1, each), residual, restriction.
+//   NSW = 1: colour 0 of row t, colour 1 of row t-2, output of row t-4: the phases of a step work on
+//            rows two apart, so that none of them waits for another one of the same step;
+//   NSW = 2: colours 0,1,0,1 of rows t, t-1, t-2, t-3, output of row t-4 (a dependent chain inside
+//            the step, hidden by the other warps; keeps the lifetime of a ring slot at 4 steps).
+template <bool WRAP, bool HASX, int CM, int NSW>
 struct Down {
-  static constexpr int HX = WRAP ? 0 : 4, HY = 3, TX = RW - 2 * HX, CO = 128;
+  static constexpr int HY = NSW == 1 ? 3 : 5;                 // rows recomputed above and below a chunk
+  static constexpr int HX = WRAP ? 0 : (NSW == 1 ? 4 : 6);    // columns recomputed left and right (even)
+  static constexpr int TX = RW - 2 * HX, CO = 128;
+  static constexpr int DOUT = 4;                              // the output of a row lags its entry by DOUT steps
   const RLevel &L;
   ColPair C;
   double *ring;            // this warp's ring (generic address)
@@ -152,12 +160,20 @@ struct Down {
     cp_commit();
   }
 
-  // one step; K = t mod 12: ring slots and window slots are compile-time constants.  Row r
-  // (tile-local) has its first column in colour 0 iff (r + HY) is even.  The three phases of a step
-  // work on rows two apart, so that none of them waits for another one of the same step (the
-  // second colour of row t-2 needs the first colour of rows t-3..t-1, done in earlier steps; the
-  // output of row t-4 needs the second colour of rows t-5..t-3).  The first steps work on rows
-  // that are not there yet (zeros): harmless, they only feed halo rows.
+  // colour COLOR of row t - D (K = t mod RD; t0 is a multiple of RD, which is even).  Row r
+  // (tile-local) has its first column in colour 0 iff (r + HY) is even.
+  template <int K, int D, int COLOR>
+  __device__ __forceinline__ void upd() {
+    constexpr int R = (K + RD - D) % RD, Rm = (K + 2 * RD - D - 1) % RD, Rp = (K + RD - D + 1) % RD;
+    constexpr bool first0 = ((K + RD - D + HY) & 1) == 0;
+    constexpr bool A = (COLOR == 0) == first0;   // the cell of this colour sits in the lane's first column
+    const double *slot = ring + R * SLOT_D;
+    if (A) xa[R] = ring_upd<WRAP, CO>(true, C, slot, lane, xb[R], xa[Rm], xa[Rp]);
+    else xb[R] = ring_upd<WRAP, CO>(false, C, slot, lane, xa[R], xb[Rm], xb[Rp]);
+  }
+
+  // one step; K = t mod 12: ring slots and window slots are compile-time constants.  The first
+  // steps work on rows that are not there yet (zeros): harmless, they only feed halo rows.
   template <int K>
   __device__ __forceinline__ void step(int t0) {
     const int t = t0 + K;
@@ -179,23 +195,20 @@ struct Down {
         b2 += rin ? (C.st ? w.x * w.x : 0.0) + (C.st == 16 ? w.y * w.y : 0.0) : 0.0;
       }
     }
-    {  // colour 0 of row t
-      constexpr int R = K % RD, Rm = (K + RD - 1) % RD, Rp = (K + 1) % RD;
-      const double *slot = ring + R * SLOT_D;
-      if (((K + HY) & 1) == 0) xa[R] = ring_upd<WRAP, CO>(true, C, slot, lane, xb[R], xa[Rm], xa[Rp]);
-      else xb[R] = ring_upd<WRAP, CO>(false, C, slot, lane, xa[R], xb[Rm], xb[Rp]);
+    if (NSW == 1) {
+      upd<K, 0, 0>();
+      upd<K, 2, 1>();
+    } else {
+      upd<K, 0, 0>();
+      upd<K, 1, 1>();
+      upd<K, 2, 0>();
+      upd<K, 3, 1>();
     }
-    {  // colour 1 of row t-2
-      constexpr int R = (K + RD - 2) % RD, Rm = (K + RD - 3) % RD, Rp = (K + RD - 1) % RD;
+    {  // output of row t - DOUT
+      constexpr int R = (K + RD - DOUT) % RD, Rm = (K + RD - DOUT - 1) % RD, Rp = (K + RD - DOUT + 1) % RD;
       const double *slot = ring + R * SLOT_D;
-      if (((K + HY) & 1) == 0) xb[R] = ring_upd<WRAP, CO>(false, C, slot, lane, xa[R], xb[Rm], xb[Rp]);
-      else xa[R] = ring_upd<WRAP, CO>(true, C, slot, lane, xb[R], xa[Rm], xa[Rp]);
-    }
-    {  // output of row t-4
-      constexpr int R = (K + RD - 4) % RD, Rm = (K + RD - 5) % RD, Rp = (K + RD - 3) % RD;
-      const double *slot = ring + R * SLOT_D;
-      const int gv = j0 + t - 4 - HY;
-      const bool rin = t >= HY + 4 && t < HY + 4 + mry && gv <= L.n2;
+      const int gv = j0 + t - DOUT - HY;
+      const bool rin = t >= HY + DOUT && t < HY + DOUT + mry && gv <= L.n2;
       const long o = (long)L.sy * gv;
       if (rin) {
         if (C.st == 16) *reinterpret_cast<double2 *>(xdst + o) = make_double2(xa[R], xb[R]);
@@ -206,7 +219,7 @@ struct Down {
       const double rw2 = slot[CO + 4];
       const double w2 = rin ? ew.y : 0.0;
       double res;
-      constexpr bool first = ((K + HY) & 1) == 0;   // colour 0 sits in the first column
+      constexpr bool first = ((K + RD - DOUT + HY) & 1) == 0;   // colour 0 sits in the first column
       if (first) {
         const double lft = WRAP ? __shfl_sync(0xffffffffu, xb[R], (lane + 31) & 31) : __shfl_up_sync(0xffffffffu, xb[R], 1);
         const double bs = slot[64 + 2 * lane] * (C.rw0 * rw2);
@@ -241,9 +254,16 @@ struct Down {
 };
 
 // ---- up --------------------------------------------------------------------------------------
-template <bool WRAP>
+// coarse-grid correction, NSW sweeps (colour 1 then 0, each).
+//   NSW = 1: colour 1 of row t, colour 0 of row t-2 (independent of each other), store of row t-2;
+//   NSW = 2: colours 1,0,1,0 of rows t, t-1, t-2, t-3, store of row t-3.
+template <bool WRAP, int NSW>
 struct Up {
-  static constexpr int HX = WRAP ? 0 : 2, HY = 2, TX = RW - 2 * HX, CO = 192;
+  static constexpr int HY = NSW == 1 ? 2 : 4;
+  static constexpr int HX = WRAP ? 0 : (NSW == 1 ? 2 : 4);
+  static constexpr int TX = RW - 2 * HX, CO = 192;
+  static constexpr int DOUT = NSW == 1 ? 2 : 3;
+  static constexpr int RPU = NSW == 1 ? 5 : 4;   // rows in flight (a slot must outlive step r + DOUT)
   const RLevel &L;
   ColPair C;
   double *ring;
@@ -270,13 +290,22 @@ struct Up {
     cp_commit();
   }
 
-  // colour 1 of row t, colour 0 of row t-2 (independent of each other), then row t-2 is final
+  template <int K, int D, int COLOR>
+  __device__ __forceinline__ void upd() {
+    constexpr int R = (K + RDU - D) % RDU, Rm = (K + 2 * RDU - D - 1) % RDU, Rp = (K + RDU - D + 1) % RDU;
+    constexpr bool first0 = ((K + RDU - D + HY) & 1) == 0;
+    constexpr bool A = (COLOR == 0) == first0;
+    const double *slot = ring + R * SLOT_U;
+    if (A) xa[R] = ring_upd<WRAP, CO>(true, C, slot, lane, xb[R], xa[Rm], xa[Rp]);
+    else xb[R] = ring_upd<WRAP, CO>(false, C, slot, lane, xa[R], xb[Rm], xb[Rp]);
+  }
+
   template <int K>
   __device__ __forceinline__ void step(int t0) {
     const int t = t0 + K;
     {
       constexpr int S = (K + 1) % RDU;
-      cp_wait<RP_U - 1>();
+      cp_wait<RPU - 1>();
       __syncwarp();
       const double *slot = ring + S * SLOT_U;
       const double2 v = *reinterpret_cast<const double2 *>(slot + 2 * lane);
@@ -284,37 +313,37 @@ struct Up {
       xa[S] = v.x + c.x;
       xb[S] = C.ld == 16 ? v.y + (c1 ? c.x : c.y) : 0.0;
     }
-    {
-      constexpr int R = K % RDU, Rm = (K + RDU - 1) % RDU, Rp = (K + 1) % RDU;
-      const double *slot = ring + R * SLOT_U;
-      if (((K + HY) & 1) == 0) xb[R] = ring_upd<WRAP, CO>(false, C, slot, lane, xa[R], xb[Rm], xb[Rp]);
-      else xa[R] = ring_upd<WRAP, CO>(true, C, slot, lane, xb[R], xa[Rm], xa[Rp]);
+    if (NSW == 1) {
+      upd<K, 0, 1>();
+      upd<K, 2, 0>();
+    } else {
+      upd<K, 0, 1>();
+      upd<K, 1, 0>();
+      upd<K, 2, 1>();
+      upd<K, 3, 0>();
     }
     {
-      constexpr int R = (K + RDU - 2) % RDU, Rm = (K + RDU - 3) % RDU, Rp = (K + RDU - 1) % RDU;
-      const double *slot = ring + R * SLOT_U;
-      if (((K + HY) & 1) == 0) xa[R] = ring_upd<WRAP, CO>(true, C, slot, lane, xb[R], xa[Rm], xa[Rp]);
-      else xb[R] = ring_upd<WRAP, CO>(false, C, slot, lane, xa[R], xb[Rm], xb[Rp]);
-      const int gv = j0 + t - 2 - HY;
-      if (t >= HY + 2 && t < HY + 2 + mry && gv <= L.n2) {
+      constexpr int R = (K + RDU - DOUT) % RDU;
+      const int gv = j0 + t - DOUT - HY;
+      if (t >= HY + DOUT && t < HY + DOUT + mry && gv <= L.n2) {
         const long o = (long)L.sy * gv;
         if (C.st == 16) *reinterpret_cast<double2 *>(xdst + o) = make_double2(xa[R], xb[R]);
         else if (C.st == 8) xdst[o] = xa[R];
       }
     }
-    issue<(K + 1 + RP_U) % RDU>(t + 1 + RP_U);
+    issue<(K + 1 + RPU) % RDU>(t + 1 + RPU);
   }
 };
 
 }  // namespace
 
 // HASX: the incoming iterate exists (level 0); below it the iterate is zero on entry
-template <bool WRAP, bool HASX, int CM>
+template <bool WRAP, bool HASX, int CM, int NSW>
 __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel L, const double *__restrict__ xin, double *__restrict__ xout,
                                                                     const double *__restrict__ b, double *__restrict__ cb, int csy, long csz,
                                                                     const double *lamq, double alpha, double *norms, int nq, int want_b,
                                                                     int ntx, int nty, int mry, const int *active, double xscale) {
-  using D = Down<WRAP, HASX, CM>;
+  using D = Down<WRAP, HASX, CM, NSW>;
   extern __shared__ __align__(16) double ring_all[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long wid = (long)blockIdx.x * WARPS_D + wib;
@@ -355,7 +384,7 @@ __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel
       s.xa[0] = v.x * xscale; s.xb[0] = v.y * xscale;
     }
   }
-  for (int t0 = 0; t0 < s.HT + 1; t0 += RD) {   // the last kept row leaves at step HT + 1 - 1
+  for (int t0 = 0; t0 < s.mry + D::HY + D::DOUT; t0 += RD) {   // the last kept row leaves at step HY + mry - 1 + DOUT
     s.template step<0>(t0); s.template step<1>(t0); s.template step<2>(t0); s.template step<3>(t0);
     s.template step<4>(t0); s.template step<5>(t0); s.template step<6>(t0); s.template step<7>(t0);
     s.template step<8>(t0); s.template step<9>(t0); s.template step<10>(t0); s.template step<11>(t0);
@@ -374,12 +403,12 @@ __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel
   }
 }
 
-template <bool WRAP>
+template <bool WRAP, int NSW>
 __global__ void __launch_bounds__(WARPS_U * 32) mg_ring_up_kernel(const RLevel L, const double *__restrict__ xin, double *__restrict__ xout,
                                                                   const double *__restrict__ b, const double *__restrict__ cx, int csy,
                                                                   long csz, const double *lamq, double alpha, int nq, int ntx, int nty,
                                                                   int mry, const int *active) {
-  using U = Up<WRAP>;
+  using U = Up<WRAP, NSW>;
   extern __shared__ __align__(16) double ring_all[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long wid = (long)blockIdx.x * WARPS_U + wib;
@@ -405,18 +434,18 @@ __global__ void __launch_bounds__(WARPS_U * 32) mg_ring_up_kernel(const RLevel L
   for (int i = 0; i < RDU; ++i) s.xa[i] = s.xb[i] = 0.0;
   for (int i = lane; i < RDU * SLOT_U; i += 32) s.ring[i] = 0.0;
   __syncwarp();
-  static_assert(RP_U == 5 && RDU == 8, "prologue below");
+  static_assert(RDU == 8 && (U::RPU == 5 || U::RPU == 4), "prologue below");
   s.template issue<0>(0); s.template issue<1>(1); s.template issue<2>(2); s.template issue<3>(3); s.template issue<4>(4);
-  s.template issue<5>(5);
+  if (U::RPU == 5) s.template issue<5>(5);
   {
-    cp_wait<RP_U - 1>();
+    cp_wait<U::RPU - 1>();
     __syncwarp();
     const double2 v = *reinterpret_cast<const double2 *>(s.ring + 2 * lane);
     const double2 c = *reinterpret_cast<const double2 *>(s.ring + 128 + 2 * lane);
     s.xa[0] = v.x + c.x;
     s.xb[0] = s.C.ld == 16 ? v.y + (s.c1 ? c.x : c.y) : 0.0;
   }
-  for (int t0 = 0; t0 < s.HT; t0 += RDU) {   // the last kept row leaves at step HT - 1
+  for (int t0 = 0; t0 < s.mry + U::HY + U::DOUT; t0 += RDU) {   // the last kept row leaves at step HY + mry - 1 + DOUT
     s.template step<0>(t0); s.template step<1>(t0); s.template step<2>(t0); s.template step<3>(t0);
     s.template step<4>(t0); s.template step<5>(t0); s.template step<6>(t0); s.template step<7>(t0);
   }
@@ -425,24 +454,24 @@ __global__ void __launch_bounds__(WARPS_U * 32) mg_ring_up_kernel(const RLevel L
 
 // rows per chunk: as long as possible (fewer recomputed halo rows) while the launch still fills the
 // machine a few times over (nact: estimate of the planes still iterating); the chunk height plus
-// its halos is a multiple of the unroll period
-static int ring_rows(int n1, int n2, int nact, int tx, int hy, int extra, int period) {
+// the steps spent on its halos and on draining the pipeline is a multiple of the unroll period
+static int ring_rows(int n1, int n2, int nact, int tx, int fixed, int period) {
   if (const char *e = getenv("SNAC_RING_MRY")) {
     const int m = atoi(e);
     if (m >= 2) return (m + 1) & ~1;
   }
   const long target = 148L * 16 * 2;   // warps
   const int ntx = (n1 + tx - 1) / tx;
+  fixed = (fixed + 1) & ~1;            // steps of a chunk = mry + fixed: a multiple of the (even) period, mry even
   int nty = 0;
-  // steps of a chunk = mry + 2 hy + extra, a multiple of the unroll period (and mry even)
   const int smin = 2 * period, smax = 264 / period * period;
   for (int st = smax; st >= smin; st -= period) {
-    const int mry = st - 2 * hy - extra;
+    const int mry = st - fixed;
     nty = (n2 + mry - 1) / mry;
     if ((long)ntx * nty * nact >= target) break;
   }
   // the shortest chunk height that still needs only nty chunks (balanced chunks)
-  int mry = smin - 2 * hy - extra;
+  int mry = smin - fixed;
   while ((n2 + mry - 1) / mry > nty) mry += period;
   return mry;
 }
@@ -457,58 +486,76 @@ static void ring_smem(K kernel, size_t bytes) {
   }
 }
 
-template <bool WRAP, bool HASX, int CM>
-static void ring_down_go(unsigned grid, cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb,
-                         int csy, long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, int ntx, int nty,
-                         int mry, const int *active, double xscale) {
-  constexpr size_t smem = (size_t)WARPS_D * RD * SLOT_D * sizeof(double);
-  ring_smem<WRAP * 8 + HASX * 4 + CM>(mg_ring_down_kernel<WRAP, HASX, CM>, smem);
-  mg_ring_down_kernel<WRAP, HASX, CM><<<grid, WARPS_D * 32, smem, st>>>(L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx,
-                                                                        nty, mry, active, xscale);
-}
-
-template <bool WRAP, bool HASX>
-static void ring_down_cm(int cm, unsigned grid, cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b,
-                         double *cb, int csy, long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, int ntx,
-                         int nty, int mry, const int *active, double xscale) {
-  if (cm == CM_FULL) ring_down_go<WRAP, HASX, CM_FULL>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
-  else if (cm == CM_X) ring_down_go<WRAP, HASX, CM_X>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
-  else ring_down_go<WRAP, HASX, CM_Y>(grid, st, L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
-}
-
-void launch_ring_down(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb, long csy,
-                      long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact, double xscale) {
-  const bool wrap = L.per1 && L.n1 == RW;
-  const int tx = wrap ? RW : RW - 8;
-  const int mry = ring_rows(L.n1, L.n2, nact, tx, 3, 2, RD);   // HT + 2 steps
-  const int ntx = (L.n1 + tx - 1) / tx, nty = (L.n2 + mry - 1) / mry;
+template <bool WRAP, bool HASX, int CM, int NSW>
+static void ring_down_go(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb, int csy,
+                         long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact,
+                         double xscale) {
+  using D = Down<WRAP, HASX, CM, NSW>;
+  const int mry = ring_rows(L.n1, L.n2, nact, D::TX, D::HY + D::DOUT, RD);
+  const int ntx = (L.n1 + D::TX - 1) / D::TX, nty = (L.n2 + mry - 1) / mry;
   const long nw = (long)ntx * nty * nq;
   const unsigned grid = (unsigned)((nw + WARPS_D - 1) / WARPS_D);
+  constexpr size_t smem = (size_t)WARPS_D * RD * SLOT_D * sizeof(double);
+  ring_smem<WRAP * 16 + HASX * 8 + CM * 2 + (NSW - 1)>(mg_ring_down_kernel<WRAP, HASX, CM, NSW>, smem);
+  mg_ring_down_kernel<WRAP, HASX, CM, NSW><<<grid, WARPS_D * 32, smem, st>>>(L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b,
+                                                                             ntx, nty, mry, active, xscale);
+}
+
+#define RING_DOWN_ARGS st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, active, nact, xscale
+template <bool WRAP, bool HASX, int NSW>
+static void ring_down_cm(int cm, cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb, long csy,
+                         long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact,
+                         double xscale) {
+  if (cm == CM_FULL) ring_down_go<WRAP, HASX, CM_FULL, NSW>(RING_DOWN_ARGS);
+  else if (cm == CM_X) ring_down_go<WRAP, HASX, CM_X, NSW>(RING_DOWN_ARGS);
+  else ring_down_go<WRAP, HASX, CM_Y, NSW>(RING_DOWN_ARGS);
+}
+
+template <int NSW>
+static void ring_down_nsw(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, double *cb, long csy,
+                          long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact,
+                          double xscale) {
+  const bool wrap = L.per1 && L.n1 == RW;
   const int cm = (L.c1 && L.c2) ? CM_FULL : (L.c1 ? CM_X : CM_Y);
   if (wrap) {
-    if (xin) ring_down_cm<true, true>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
-    else ring_down_cm<true, false>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
+    if (xin) ring_down_cm<true, true, NSW>(cm, RING_DOWN_ARGS);
+    else ring_down_cm<true, false, NSW>(cm, RING_DOWN_ARGS);
   } else {
-    if (xin) ring_down_cm<false, true>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
-    else ring_down_cm<false, false>(cm, grid, st, L, xin, xout, b, cb, (int)csy, csz, lamq, alpha, norms, nq, want_b, ntx, nty, mry, active, xscale);
+    if (xin) ring_down_cm<false, true, NSW>(cm, RING_DOWN_ARGS);
+    else ring_down_cm<false, false, NSW>(cm, RING_DOWN_ARGS);
   }
 }
 
-void launch_ring_up(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, const double *cx, long csy,
-                    long csz, const double *lamq, double alpha, int nq, const int *active, int nact) {
-  const bool wrap = L.per1 && L.n1 == RW;
-  const int tx = wrap ? RW : RW - 4;
-  const int mry = ring_rows(L.n1, L.n2, nact, tx, 2, 0, RDU);
-  const int ntx = (L.n1 + tx - 1) / tx, nty = (L.n2 + mry - 1) / mry;
+void launch_ring_down(cudaStream_t st, const RLevel &L, int nsweep, const double *xin, double *xout, const double *b, double *cb, long csy,
+                      long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact,
+                      double xscale) {
+  if (nsweep == 1) ring_down_nsw<1>(RING_DOWN_ARGS);
+  else ring_down_nsw<2>(RING_DOWN_ARGS);
+}
+#undef RING_DOWN_ARGS
+
+template <bool WRAP, int NSW>
+static void ring_up_go(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, const double *cx, long csy,
+                       long csz, const double *lamq, double alpha, int nq, const int *active, int nact) {
+  using U = Up<WRAP, NSW>;
+  const int mry = ring_rows(L.n1, L.n2, nact, U::TX, U::HY + U::DOUT, RDU);
+  const int ntx = (L.n1 + U::TX - 1) / U::TX, nty = (L.n2 + mry - 1) / mry;
   const long nw = (long)ntx * nty * nq;
   const unsigned grid = (unsigned)((nw + WARPS_U - 1) / WARPS_U);
   constexpr size_t smem = (size_t)WARPS_U * RDU * SLOT_U * sizeof(double);
-  if (wrap) {
-    ring_smem<100>(mg_ring_up_kernel<true>, smem);
-    mg_ring_up_kernel<true><<<grid, WARPS_U * 32, smem, st>>>(L, xin, xout, b, cx, (int)csy, csz, lamq, alpha, nq, ntx, nty, mry, active);
+  ring_smem<100 + WRAP * 2 + (NSW - 1)>(mg_ring_up_kernel<WRAP, NSW>, smem);
+  mg_ring_up_kernel<WRAP, NSW><<<grid, WARPS_U * 32, smem, st>>>(L, xin, xout, b, cx, (int)csy, csz, lamq, alpha, nq, ntx, nty, mry, active);
+}
+
+void launch_ring_up(cudaStream_t st, const RLevel &L, int nsweep, const double *xin, double *xout, const double *b, const double *cx,
+                    long csy, long csz, const double *lamq, double alpha, int nq, const int *active, int nact) {
+  const bool wrap = L.per1 && L.n1 == RW;
+  if (nsweep == 1) {
+    if (wrap) ring_up_go<true, 1>(st, L, xin, xout, b, cx, csy, csz, lamq, alpha, nq, active, nact);
+    else ring_up_go<false, 1>(st, L, xin, xout, b, cx, csy, csz, lamq, alpha, nq, active, nact);
   } else {
-    ring_smem<101>(mg_ring_up_kernel<false>, smem);
-    mg_ring_up_kernel<false><<<grid, WARPS_U * 32, smem, st>>>(L, xin, xout, b, cx, (int)csy, csz, lamq, alpha, nq, ntx, nty, mry, active);
+    if (wrap) ring_up_go<true, 2>(st, L, xin, xout, b, cx, csy, csz, lamq, alpha, nq, active, nact);
+    else ring_up_go<false, 2>(st, L, xin, xout, b, cx, csy, csz, lamq, alpha, nq, active, nact);
   }
 }
 

@@ -162,8 +162,6 @@ SOLVE_CASES = [("channel", 0, {}, False), ("channel", 1, {}, False), ("channel",
                ("channel", 1, dict(dims=(1, 1, 1), ng=(4, 200, 72)), False),
                ("tgv", 2, dict(n=64), False),
                # larger planes: strips with column halos, odd sizes, semi-coarsening on stretched walls
-               ("cavity", 2, dict(dims=(1, 1, 1), ng=(75, 6, 90)), False),
-               ("channel", 2, dict(dims=(1, 1, 1), ng=(160, 6, 130)), False),
                ("tgv", 2, dict(n=128), False)]
 
 
@@ -182,15 +180,26 @@ STREAM_CASES = [("channel", 2, dict(dims=(1, 1, 1), ng=(96, 8, 80))), ("channel"
 
 @pytest.mark.parametrize("kind,fa,kw", STREAM_CASES)
 @pytest.mark.parametrize("cells", [300, 1500])
-def test_solver_streaming_kernels(tmp_path, monkeypatch, kind, fa, kw, cells):
+@pytest.mark.parametrize("sweeps", [1, 2])
+def test_solver_streaming_kernels(tmp_path, monkeypatch, kind, fa, kw, cells, sweeps):
     monkeypatch.setenv("SNAC_MG_SMEM_CELLS", str(cells))
-    _solve_and_compare(tmp_path, kind, fa, kw, False)
+    _solve_and_compare(tmp_path, kind, fa, kw, False, sweeps=sweeps)
 
 
-def _solve_and_compare(tmp_path, kind, fa, kw, generic):
+# stretched / anisotropic planes with odd sizes on several levels: V(1,1) with point smoothing stalls
+# or diverges on these (numpy prototype and GPU agree), V(2,2) converges at ~0.2 per cycle
+HARD_CASES = [("cavity", 2, dict(dims=(1, 1, 1), ng=(75, 6, 90))), ("channel", 2, dict(dims=(1, 1, 1), ng=(160, 6, 130)))]
+
+
+@pytest.mark.parametrize("kind,fa,kw", HARD_CASES)
+def test_solver_two_sweeps_on_stretched_planes(tmp_path, kind, fa, kw):
+    _solve_and_compare(tmp_path, kind, fa, kw, False, sweeps=2)
+
+
+def _solve_and_compare(tmp_path, kind, fa, kw, generic, sweeps=0):
     case = cases.make(kind, str(tmp_path), fft_axis=fa, **kw)
     fields = cases.random_fields(case, seed=7)
-    o, g = make_pair(case, fields, tol=1e-11, maxiter=200, mg_generic=generic)
+    o, g = make_pair(case, fields, tol=1e-11, maxiter=200, mg_generic=generic, mg_npre=sweeps, mg_npost=sweeps)
     o.bounduvw(False)
     o.dt = 0.01
     dtrk = float(RK[0].sum()) * o.dt
