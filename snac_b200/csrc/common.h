@@ -415,6 +415,7 @@ enum ProfClass : int {
 struct Ctx {
   snac_params prm;
   bool prof_on = false;
+  double prof_overhead_ms = 0.0;       // event-pair time around an empty launch on an idle stream (subtracted per scope)
   double prof_ms[PC_COUNT] = {0};
   long long prof_n[PC_COUNT] = {0};
   double prof_units[PC_COUNT] = {0};   // grid points processed (active planes only for the solver kernels)
@@ -451,6 +452,7 @@ struct Ctx {
   std::unique_ptr<MGSolver> ssolver[SNAC_MAX_SCAL];
   double fs[SNAC_MAX_SCAL] = {0};                   // accumulated scalar forcing (src/main.f90:913)
   // reductions
+  DevBuf xfer;              // dense staging buffer of snac_upload / snac_download
   DevBuf red;               // scratch for chkdt/chkdiv
   double *h_red = nullptr;  // pinned
   double **d_slots = nullptr;
@@ -470,7 +472,7 @@ struct ProfScope {
     cudaEventSynchronize(c.prof_ev[1]);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c.prof_ev[0], c.prof_ev[1]);
-    c.prof_ms[cls] += ms;
+    if (c.launches > l0) c.prof_ms[cls] += ms > c.prof_overhead_ms ? ms - c.prof_overhead_ms : 0.0;
     c.prof_n[cls] += c.launches - l0;
   }
 };
