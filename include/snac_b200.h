@@ -137,6 +137,13 @@ SNAC_API int snac_rk_mom(snac_handle *h, int irk, double dt);            /* rk_m
 SNAC_API int snac_rk_scal(snac_handle *h, int irk, double dt, int iscal);/* rk_scal + bulk_forcing_s, src/rk.f90:130-204 */
 SNAC_API int snac_bounduvw(snac_handle *h, int is_correc);               /* bounduvw, src/bound.f90:8-66 */
 SNAC_API int snac_boundp(snac_handle *h, int field);                     /* boundp, src/bound.f90:68-106 */
+/* inflow planes of one face of box `rank` (u_in/v_in/w_in%{x,y,z}(:,:,ib), src/main.f90:232-240,594-632):
+ * three column-major planes with ghosts, (n_a+2) x (n_b+2), a < b the in-plane directions; veln is the
+ * component normal to the face, velt1/velt2 the other two in x<y<z order (init_inflow, src/initflow.f90:369-429).
+ * idir = 0..2, ib = 0 (lower) or 1 (upper); the face must be a physical boundary with cbcvel 'D' for the
+ * normal component (is_bound_inflow, src/main.f90:596). */
+SNAC_API int snac_set_inflow(snac_handle *h, int rank, int idir, int ib, const double *veln, const double *velt1, const double *velt2);
+SNAC_API int snac_inflow(snac_handle *h, int is_correc);                 /* inflow, src/bound.f90:438-477; no-op without planes */
 SNAC_API int snac_fillps(snac_handle *h, double dtrk);                   /* fillps, src/fillps.f90:7-54 -> RHS */
 SNAC_API int snac_updt_rhs(snac_handle *h);                              /* updt_rhs, src/bound.f90:543-585 on RHS */
 SNAC_API int snac_fft(snac_handle *h, int dir);  /* fft, src/fft.f90:85-94: dir=+1 RHS -> RHS_HAT; dir=-1 PO -> PP, times normfft (src/main.f90:1017-1020) */

@@ -34,16 +34,17 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """``defines``/``out``: a tuning variant of the library (extra -D flags) written to ``out``."""
+    if out is None and not force and not _stale():
         return LIB
     nv = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out).replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nv, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nv, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,11 +58,11 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         for _, err in res:
             sys.stderr.write(err)
     cmd = [nv, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-o", LIB, *[o for o, _ in res]]
+           "-o", out or LIB, *[o for o, _ in res]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

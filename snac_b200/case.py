@@ -73,3 +73,29 @@ def initial_fields(case: Case, ranks=None, noise: bool = False):
                           float(p.scalf[i])) for i in range(p.nscal)]
         out[r] = dict(u=u, v=v, w=w, p=pr, s=s)
     return out
+
+
+def inflow_planes(case: Case, ranks=None):
+    """Inflow planes of the boxes (reference src/main.f90:594-632): returns ``(is_bound_inflow, planes)``
+    with ``is_bound_inflow[r]`` a (3,2) bool array ``[idir, ib]`` and ``planes[r][(idir, ib)] = (veln,
+    velt1, velt2)``: ghosted planes of the normal and the two tangential components (x<y<z order)."""
+    p, world = case.params, case.world
+    ranks = list(range(world.nrank)) if ranks is None else list(ranks)
+    flags, planes = {}, {}
+    for r in ranks:
+        box, g = world.boxes[r], case.grids[r]
+        b = p.blocks[box.block]
+        flags[r] = np.zeros((3, 2), bool)
+        planes[r] = {}
+        for idir in range(3):
+            t = [d for d in range(3) if d != idir]
+            for ib in range(2):
+                on = bool(box.is_bound[idir, ib]) and int(b.inflow_type[ib, idir]) > 0 and b.cbcvel[ib, idir, idir] == "D"
+                flags[r][idir, ib] = on
+                if on:
+                    planes[r][(idir, ib)] = _if.init_inflow(
+                        int(b.inflow_type[ib, idir]), [world.periods[t[0]], world.periods[t[1]]],
+                        [box.lo[t[0]], box.lo[t[1]]], [box.hi[t[0]], box.hi[t[1]]],
+                        [b.lmin[t[0]], b.lmin[t[1]]], [b.lmax[t[0]], b.lmax[t[1]]],
+                        g.rc(t[0]), g.rf(t[0]), g.rc(t[1]), g.rf(t[1]), float(b.bcvel[ib, idir, idir]), 1.0, p.visc)
+    return flags, planes

@@ -544,6 +544,60 @@ static void do_bounduvw(Ctx &ctx, bool is_correc) {
   ctx.ex_uvw[ctx.par].run_all(ctx);
   ctx.bc_uvw[ctx.par][is_correc ? 1 : 0].run(ctx);
 }
+// inflow (src/bound.f90:438-477): prescribed velocity planes on the 'D' faces flagged by
+// is_bound_inflow (src/main.f90:594-632); the normal component only when not correcting
+static void build_inflow(Ctx &ctx) {
+  for (int par = 0; par < 2; ++par)
+    for (int ic = 0; ic < 2; ++ic) {
+      std::vector<FaceOp> ops[3];
+      for (auto &bp : ctx.boxes) {
+        Box &b = *bp;
+        double *fld[3] = {b.u[par].p, b.v[par].p, b.w[par].p};
+        for (int idir = 0; idir < 3; ++idir)
+          for (int ib = 0; ib < 2; ++ib) {
+            if (!b.is_inflow[idir][ib]) continue;
+            const int a = idir == 0 ? 1 : 0, bb = idir == 2 ? 1 : 2;
+            for (int c = 0; c < 3; ++c) {
+              const bool normal = (c == idir);
+              if (normal && ic) continue;
+              FaceOp op;
+              op.p = fld[c];
+              op.sd = b.g.st(idir); op.sa = b.g.st(a); op.sb = b.g.st(bb);
+              op.n = b.g.n[idir]; op.na = b.g.n[a] + 2; op.nb = b.g.n[bb] + 2;
+              op.factor = 0.0; op.sgn = 0.0;
+              op.plane = b.inflow[idir][ib][c].p();
+              op.kind = normal ? (ib == 0 ? FACE_INFLOW_N_LO : FACE_INFLOW_N_HI) : (ib == 0 ? FACE_INFLOW_T_LO : FACE_INFLOW_T_HI);
+              ops[idir].push_back(op);
+            }
+          }
+      }
+      ctx.bc_inflow[par][ic].upload(ops);
+    }
+  ctx.inflow_dirty = false;
+}
+static void do_inflow(Ctx &ctx, bool is_correc) {
+  if (!ctx.has_inflow) return;
+  ProfScope ps(ctx, PC_HALO_BC);
+  if (ctx.inflow_dirty) build_inflow(ctx);
+  ctx.bc_inflow[ctx.par][is_correc ? 1 : 0].run(ctx);
+}
+static void set_inflow(Ctx &ctx, int rank, int idir, int ib, const double *veln, const double *velt1, const double *velt2) {
+  if (idir < 0 || idir > 2 || ib < 0 || ib > 1) throw Error("set_inflow: idir must be 0..2 and ib 0 or 1");
+  if (ctx.prm.impdiff) throw Error("set_inflow: inflow planes with implicit diffusion are not supported");
+  Box &b = ctx.box_of_rank(rank);
+  if (!b.info.is_bound[idir][ib] || b.info.cbcvel[idir][idir][ib] != 'D')
+    throw Error("set_inflow: the face is not a physical boundary with a Dirichlet normal velocity (src/main.f90:596)");
+  const int a = idir == 0 ? 1 : 0, bb = idir == 2 ? 1 : 2;
+  const size_t n = (size_t)(b.g.n[a] + 2) * (b.g.n[bb] + 2);
+  // veln is the component normal to the face, velt1/velt2 the other two in x<y<z order (src/main.f90:601-621)
+  const double *src[3];
+  src[idir] = veln; src[a] = velt1; src[bb] = velt2;
+  SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+  for (int c = 0; c < 3; ++c) b.inflow[idir][ib][c].upload(std::vector<double>(src[c], src[c] + n));
+  b.is_inflow[idir][ib] = true;
+  ctx.has_inflow = true;
+  ctx.inflow_dirty = true;
+}
 static void do_boundp(Ctx &ctx, int field) {
   ProfScope ps(ctx, PC_HALO_BC);
   if (field == SNAC_FIELD_P) { ctx.ex_p.run_all(ctx); ctx.bc_p.run(ctx); }
@@ -676,6 +730,7 @@ static void substep(Ctx &ctx, int irk, double dt) {
   if (ctx.prm.impdiff)   // src/main.f90:947-994
     for (int c = 0; c < 3; ++c) do_helmholtz(ctx, *ctx.usolver[c][ctx.par], c, 1.0 / alpha);
   do_bounduvw(ctx, false);
+  do_inflow(ctx, false);   // src/main.f90:999
   double pts = 0.0;
   for (auto &b : ctx.boxes) pts += (double)b->g.n[0] * b->g.n[1] * b->g.n[2];
   {
@@ -704,6 +759,7 @@ static void substep(Ctx &ctx, int irk, double dt) {
     for (auto &b : ctx.boxes) launch_correc_updt(ctx, *b, dtrk, alpha, true, true);
   }
   do_bounduvw(ctx, true);
+  do_inflow(ctx, true);    // src/main.f90:1028
   do_boundp(ctx, SNAC_FIELD_P);
 }
 
@@ -844,6 +900,10 @@ int snac_rk_mom(snac_handle *h, int irk, double dt) { SNAC_TRY(h, do_rk_mom(h->c
 int snac_rk_scal(snac_handle *h, int irk, double dt, int iscal) { SNAC_TRY(h, do_rk_scal(h->ctx, irk, dt, iscal)) }
 int snac_bounduvw(snac_handle *h, int is_correc) { SNAC_TRY(h, do_bounduvw(h->ctx, is_correc != 0)) }
 int snac_boundp(snac_handle *h, int field) { SNAC_TRY(h, do_boundp(h->ctx, field)) }
+int snac_set_inflow(snac_handle *h, int rank, int idir, int ib, const double *veln, const double *velt1, const double *velt2) {
+  SNAC_TRY(h, set_inflow(h->ctx, rank, idir, ib, veln, velt1, velt2))
+}
+int snac_inflow(snac_handle *h, int is_correc) { SNAC_TRY(h, do_inflow(h->ctx, is_correc != 0)) }
 int snac_fillps(snac_handle *h, double dtrk) {
   SNAC_TRY(h, for (auto &b : h->ctx.boxes) launch_fillps(h->ctx, *b, dtrk))
 }

@@ -39,6 +39,11 @@ __global__ void face_ops_kernel(const FaceOp *ops) {
         q[n * sd] = v;
         q[(n + 1) * sd] = v;
       } break;
+      // inflow (src/bound.f90:456-472)
+      case FACE_INFLOW_N_LO: q[0] = op.plane[t]; break;
+      case FACE_INFLOW_N_HI: q[n * sd] = op.plane[t]; break;
+      case FACE_INFLOW_T_LO: q[0] = 2.0 * op.plane[t] - q[sd]; break;
+      case FACE_INFLOW_T_HI: q[(n + 1) * sd] = 2.0 * op.plane[t] - q[n * sd]; break;
     }
   }
 }

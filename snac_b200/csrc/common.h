@@ -112,7 +112,12 @@ enum FaceKind : int {
   FACE_STAG_D_LO = 2,  // q(0) = factor
   FACE_STAG_D_HI = 3,  // q(n) = factor ; q(n+1) = q(n-1)
   FACE_STAG_N_LO = 4,  // q(0) = factor + q(1)
-  FACE_STAG_N_HI = 5   // q(n) = factor + q(n-1) ; q(n+1) = q(n)
+  FACE_STAG_N_HI = 5,  // q(n) = factor + q(n-1) ; q(n+1) = q(n)
+  // inflow planes (src/bound.f90:438-477); `plane` holds the prescribed velocity per face cell
+  FACE_INFLOW_N_LO = 6,  // q(0)   = plane
+  FACE_INFLOW_N_HI = 7,  // q(n)   = plane
+  FACE_INFLOW_T_LO = 8,  // q(0)   = -q(1) + 2 plane
+  FACE_INFLOW_T_HI = 9   // q(n+1) = -q(n) + 2 plane
 };
 
 struct FaceOp {
@@ -121,6 +126,7 @@ struct FaceOp {
   int n, na, nb;  // interior size along the normal; in-plane extents (full ghost extents)
   int kind;
   double factor, sgn;
+  const double *plane = nullptr;   // inflow kinds: dense (na, nb) plane, first index fastest
 };
 
 template <class T>
@@ -362,6 +368,8 @@ struct Box {
   // axis (else 1), and the boundary coefficient of init_bc_rhs per face
   Dev1 wq[3], gq[3];
   double cbp[3][2];
+  Dev1 inflow[3][2][3];     // inflow planes [idir][ib][component u,v,w] (u_in/v_in/w_in%{x,y,z}, src/main.f90:232-240)
+  bool is_inflow[3][2] = {{false, false}, {false, false}, {false, false}};
   bool pp_is_po = false;    // 3-D solve: pp aliases the solver iterate
   double *pp_ptr() const { return pp_is_po ? po.p : pp.p; }
   BoxGeom geom() const;
@@ -442,6 +450,8 @@ struct Ctx {
   // exchanges / BC fills
   Exchange ex_uvw[2], ex_p, ex_pp;
   FaceFill bc_uvw[2][2];   // [parity][is_correc]
+  FaceFill bc_inflow[2][2];
+  bool has_inflow = false, inflow_dirty = false;
   FaceFill bc_p, bc_pp;
   Exchange ex_s[SNAC_MAX_SCAL];
   FaceFill bc_s[SNAC_MAX_SCAL];

@@ -30,15 +30,37 @@
 // zero, subnormal or infinite here).
 #include "common.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace snac {
 
 namespace {
 constexpr int RW = 64;    // columns per warp
-constexpr int RD = 12;    // ring slots = window slots = unroll period of the march, down kernel
-constexpr int RDU = 8;    // the same for the up kernel (rows leave the window earlier there)
-constexpr int RP_D = 6;   // rows in flight ahead of the one entering the window (a slot must outlive the last use of its row)
+#ifndef SNAC_RING_RD
+#define SNAC_RING_RD 10
+#endif
+#ifndef SNAC_RING_RPD
+#define SNAC_RING_RPD 4
+#endif
+// ring slots = window slots = unroll period of the march, down kernel: 10 slots x 136 doubles x 4 warps
+// = 43.5 KB per CTA, so that five CTAs (20 warps) fit on an SM (12 slots: four)
+constexpr int RD = SNAC_RING_RD;
+#ifndef SNAC_RING_RDU
+#define SNAC_RING_RDU 8
+#endif
+#ifndef SNAC_RING_MINB_D
+#define SNAC_RING_MINB_D 1
+#endif
+#ifndef SNAC_RING_MINB_U
+#define SNAC_RING_MINB_U 1
+#endif
+constexpr int RDU = SNAC_RING_RDU;    // the same for the up kernel (rows leave the window earlier there)
+// rows in flight ahead of the one entering the window; a slot is refilled at the end of step t with row
+// t + 1 + RP_D, i.e. it must hold a row last used at step t - 1 or earlier: RD - RP_D - 1 >= DOUT + 1
+constexpr int RP_D = SNAC_RING_RPD;
+static_assert(RD % 2 == 0 && RD - RP_D - 1 >= 5 && RP_D >= 2 && RP_D <= 6 && (RD == 8 || RD == 10 || RD == 12), "ring geometry");
+static_assert(RDU == 6 || RDU == 8, "ring geometry");
 constexpr int WARPS_D = 4, WARPS_U = 2;   // warps per CTA (independent of each other)
 constexpr int SLOT_D = 64 + 64 + 8;       // doubles per ring slot, down: x, b, coefficients
 constexpr int SLOT_U = 64 + 64 + 64 + 8;  // up: x, b, coarse x, coefficients
@@ -263,7 +285,7 @@ struct Up {
   static constexpr int HX = WRAP ? 0 : (NSW == 1 ? 2 : 4);
   static constexpr int TX = RW - 2 * HX, CO = 192;
   static constexpr int DOUT = NSW == 1 ? 2 : 3;
-  static constexpr int RPU = NSW == 1 ? 5 : 4;   // rows in flight (a slot must outlive step r + DOUT)
+  static constexpr int RPU = RDU - DOUT - 1;   // rows in flight (a slot must outlive step r + DOUT): 5 / 4 for RDU = 8
   const RLevel &L;
   ColPair C;
   double *ring;
@@ -339,7 +361,7 @@ struct Up {
 
 // HASX: the incoming iterate exists (level 0); below it the iterate is zero on entry
 template <bool WRAP, bool HASX, int CM, int NSW>
-__global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel L, const double *__restrict__ xin, double *__restrict__ xout,
+__global__ void __launch_bounds__(WARPS_D * 32, SNAC_RING_MINB_D) mg_ring_down_kernel(const RLevel L, const double *__restrict__ xin, double *__restrict__ xout,
                                                                     const double *__restrict__ b, double *__restrict__ cb, int csy, long csz,
                                                                     const double *lamq, double alpha, double *norms, int nq, int want_b,
                                                                     int ntx, int nty, int mry, const int *active, double xscale) {
@@ -373,9 +395,12 @@ __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel
   // the ring slots of rows "before the first" are read by the first steps: they must hold finite numbers
   for (int i = lane; i < RD * SLOT_D; i += 32) s.ring[i] = 0.0;
   __syncwarp();
-  static_assert(RP_D == 6 && RD == 12, "prologue below");
-  s.template issue<0>(0); s.template issue<1>(1); s.template issue<2>(2); s.template issue<3>(3); s.template issue<4>(4);
-  s.template issue<5>(5); s.template issue<6>(6);
+  // rows 0 .. RP_D are in flight before the march starts
+  s.template issue<0>(0); s.template issue<1>(1); s.template issue<2>(2);
+  if (RP_D >= 3) s.template issue<3>(3);
+  if (RP_D >= 4) s.template issue<4>(4);
+  if (RP_D >= 5) s.template issue<5>(5);
+  if (RP_D >= 6) s.template issue<6>(6);
   {  // row 0 enters the window
     cp_wait<RP_D - 1>();
     __syncwarp();
@@ -387,7 +412,8 @@ __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel
   for (int t0 = 0; t0 < s.mry + D::HY + D::DOUT; t0 += RD) {   // the last kept row leaves at step HY + mry - 1 + DOUT
     s.template step<0>(t0); s.template step<1>(t0); s.template step<2>(t0); s.template step<3>(t0);
     s.template step<4>(t0); s.template step<5>(t0); s.template step<6>(t0); s.template step<7>(t0);
-    s.template step<8>(t0); s.template step<9>(t0); s.template step<10>(t0); s.template step<11>(t0);
+    if (RD >= 10) { s.template step<8 % RD>(t0); s.template step<9 % RD>(t0); }
+    if (RD == 12) { s.template step<10 % RD>(t0); s.template step<11 % RD>(t0); }
   }
   cp_wait<0>();
   if (norms) {
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(WARPS_D * 32) mg_ring_down_kernel(const RLevel
 }
 
 template <bool WRAP, int NSW>
-__global__ void __launch_bounds__(WARPS_U * 32) mg_ring_up_kernel(const RLevel L, const double *__restrict__ xin, double *__restrict__ xout,
+__global__ void __launch_bounds__(WARPS_U * 32, SNAC_RING_MINB_U) mg_ring_up_kernel(const RLevel L, const double *__restrict__ xin, double *__restrict__ xout,
                                                                   const double *__restrict__ b, const double *__restrict__ cx, int csy,
                                                                   long csz, const double *lamq, double alpha, int nq, int ntx, int nty,
                                                                   int mry, const int *active) {
@@ -434,9 +460,11 @@ __global__ void __launch_bounds__(WARPS_U * 32) mg_ring_up_kernel(const RLevel L
   for (int i = 0; i < RDU; ++i) s.xa[i] = s.xb[i] = 0.0;
   for (int i = lane; i < RDU * SLOT_U; i += 32) s.ring[i] = 0.0;
   __syncwarp();
-  static_assert(RDU == 8 && (U::RPU == 5 || U::RPU == 4), "prologue below");
-  s.template issue<0>(0); s.template issue<1>(1); s.template issue<2>(2); s.template issue<3>(3); s.template issue<4>(4);
-  if (U::RPU == 5) s.template issue<5>(5);
+  static_assert(U::RPU >= 2 && U::RPU <= 5, "prologue below");
+  s.template issue<0>(0); s.template issue<1>(1); s.template issue<2>(2);
+  if (U::RPU >= 3) s.template issue<3>(3);
+  if (U::RPU >= 4) s.template issue<4>(4);
+  if (U::RPU >= 5) s.template issue<5>(5);
   {
     cp_wait<U::RPU - 1>();
     __syncwarp();
@@ -447,33 +475,53 @@ __global__ void __launch_bounds__(WARPS_U * 32) mg_ring_up_kernel(const RLevel L
   }
   for (int t0 = 0; t0 < s.mry + U::HY + U::DOUT; t0 += RDU) {   // the last kept row leaves at step HY + mry - 1 + DOUT
     s.template step<0>(t0); s.template step<1>(t0); s.template step<2>(t0); s.template step<3>(t0);
-    s.template step<4>(t0); s.template step<5>(t0); s.template step<6>(t0); s.template step<7>(t0);
+    s.template step<4>(t0); s.template step<5>(t0);
+    if (RDU == 8) { s.template step<6 % RDU>(t0); s.template step<7 % RDU>(t0); }
   }
   cp_wait<0>();
 }
 
-// rows per chunk: as long as possible (fewer recomputed halo rows) while the launch still fills the
-// machine a few times over (nact: estimate of the planes still iterating); the chunk height plus
-// the steps spent on its halos and on draining the pipeline is a multiple of the unroll period
-static int ring_rows(int n1, int n2, int nact, int tx, int fixed, int period) {
+// rows per chunk.  Every warp of a launch marches the same number of steps at a pace set by latencies,
+// not by throughput, so the launch lasts (waves of CTAs) x (steps per chunk): the chunk height is the
+// one that minimises that product for the planes still iterating (nact: an estimate), given the
+// CTA slots of the device (slots = SMs x resident CTAs per SM of this kernel).  Short chunks recompute
+// relatively more halo rows, long ones leave the last wave half empty.  The chunk height plus the
+// steps spent on its halos and on draining the pipeline is a multiple of the unroll period.
+static int ring_rows(int n1, int n2, int nact, int tx, int fixed, int period, int warps_per_cta, long slots) {
   if (const char *e = getenv("SNAC_RING_MRY")) {
     const int m = atoi(e);
     if (m >= 2) return (m + 1) & ~1;
   }
-  const long target = 148L * 16 * 2;   // warps
   const int ntx = (n1 + tx - 1) / tx;
   fixed = (fixed + 1) & ~1;            // steps of a chunk = mry + fixed: a multiple of the (even) period, mry even
-  int nty = 0;
   const int smin = 2 * period, smax = 264 / period * period;
-  for (int st = smax; st >= smin; st -= period) {
-    const int mry = st - fixed;
-    nty = (n2 + mry - 1) / mry;
-    if ((long)ntx * nty * nact >= target) break;
+  double best = 1e300;
+  int best_mry = smin - fixed;
+  for (int st = smin; st <= smax; st += period) {
+    int mry = st - fixed;
+    if (mry < 2) continue;
+    const int nty = (n2 + mry - 1) / mry;
+    // the shortest chunk height that still needs only nty chunks (balanced chunks)
+    while (mry - period >= 2 && (n2 + (mry - period) - 1) / (mry - period) == nty) mry -= period;
+    const long ctas = ((long)ntx * nty * std::max(nact, 1) + warps_per_cta - 1) / warps_per_cta;
+    const long waves = (ctas + slots - 1) / slots;
+    // a last wave that is nearly empty costs as much as a full one; add a small share of the total
+    // work so that, between equal wave counts, the launch with less recomputation wins
+    const int steps = mry + fixed + 6;   // + set-up of a warp, in units of a step
+    const double cost = (double)waves * steps + 0.05 * (double)ctas / slots * steps;
+    if (cost < best) { best = cost; best_mry = mry; }
+    if (nty == 1) break;
   }
-  // the shortest chunk height that still needs only nty chunks (balanced chunks)
-  int mry = smin - fixed;
-  while ((n2 + mry - 1) / mry > nty) mry += period;
-  return mry;
+  return best_mry;
+}
+
+template <class K>
+static long ring_slots(K kernel, int threads, size_t smem) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return (long)sms * per_sm;
 }
 
 // opt in to more than 48 KB of dynamic shared memory, once per kernel (TAG makes the flag per kernel)
@@ -491,12 +539,13 @@ static void ring_down_go(cudaStream_t st, const RLevel &L, const double *xin, do
                          long csz, const double *lamq, double alpha, double *norms, int nq, int want_b, const int *active, int nact,
                          double xscale) {
   using D = Down<WRAP, HASX, CM, NSW>;
-  const int mry = ring_rows(L.n1, L.n2, nact, D::TX, D::HY + D::DOUT, RD);
+  constexpr size_t smem = (size_t)WARPS_D * RD * SLOT_D * sizeof(double);
+  ring_smem<WRAP * 16 + HASX * 8 + CM * 2 + (NSW - 1)>(mg_ring_down_kernel<WRAP, HASX, CM, NSW>, smem);
+  static const long slots = ring_slots(mg_ring_down_kernel<WRAP, HASX, CM, NSW>, WARPS_D * 32, smem);
+  const int mry = ring_rows(L.n1, L.n2, nact, D::TX, D::HY + D::DOUT, RD, WARPS_D, slots);
   const int ntx = (L.n1 + D::TX - 1) / D::TX, nty = (L.n2 + mry - 1) / mry;
   const long nw = (long)ntx * nty * nq;
   const unsigned grid = (unsigned)((nw + WARPS_D - 1) / WARPS_D);
-  constexpr size_t smem = (size_t)WARPS_D * RD * SLOT_D * sizeof(double);
-  ring_smem<WRAP * 16 + HASX * 8 + CM * 2 + (NSW - 1)>(mg_ring_down_kernel<WRAP, HASX, CM, NSW>, smem);
   mg_ring_down_kernel<WRAP, HASX, CM, NSW><<<grid, WARPS_D * 32, smem, st>>>(L, xin, xout, b, cb, csy, csz, lamq, alpha, norms, nq, want_b,
                                                                              ntx, nty, mry, active, xscale);
 }
@@ -538,12 +587,13 @@ template <bool WRAP, int NSW>
 static void ring_up_go(cudaStream_t st, const RLevel &L, const double *xin, double *xout, const double *b, const double *cx, long csy,
                        long csz, const double *lamq, double alpha, int nq, const int *active, int nact) {
   using U = Up<WRAP, NSW>;
-  const int mry = ring_rows(L.n1, L.n2, nact, U::TX, U::HY + U::DOUT, RDU);
+  constexpr size_t smem = (size_t)WARPS_U * RDU * SLOT_U * sizeof(double);
+  ring_smem<100 + WRAP * 2 + (NSW - 1)>(mg_ring_up_kernel<WRAP, NSW>, smem);
+  static const long slots = ring_slots(mg_ring_up_kernel<WRAP, NSW>, WARPS_U * 32, smem);
+  const int mry = ring_rows(L.n1, L.n2, nact, U::TX, U::HY + U::DOUT, RDU, WARPS_U, slots);
   const int ntx = (L.n1 + U::TX - 1) / U::TX, nty = (L.n2 + mry - 1) / mry;
   const long nw = (long)ntx * nty * nq;
   const unsigned grid = (unsigned)((nw + WARPS_U - 1) / WARPS_U);
-  constexpr size_t smem = (size_t)WARPS_U * RDU * SLOT_U * sizeof(double);
-  ring_smem<100 + WRAP * 2 + (NSW - 1)>(mg_ring_up_kernel<WRAP, NSW>, smem);
   mg_ring_up_kernel<WRAP, NSW><<<grid, WARPS_U * 32, smem, st>>>(L, xin, xout, b, cx, (int)csy, csz, lamq, alpha, nq, ntx, nty, mry, active);
 }
 

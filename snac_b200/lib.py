@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsnacb200.so")
+# SNAC_B200_LIB: an alternative build of the same library (kernel-tuning experiments, tools/build_variant.py)
+LIB_PATH = os.environ.get("SNAC_B200_LIB") or os.path.join(HERE, "libsnacb200.so")
 
 SNAC_ABI_VERSION = 1
 SNAC_MAX_SCAL = 8
@@ -68,6 +69,8 @@ EXPORTS = {
     "snac_rk_scal": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "snac_bounduvw": (C.c_int, [C.c_void_p, C.c_int]),
     "snac_boundp": (C.c_int, [C.c_void_p, C.c_int]),
+    "snac_set_inflow": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snac_inflow": (C.c_int, [C.c_void_p, C.c_int]),
     "snac_fillps": (C.c_int, [C.c_void_p, C.c_double]),
     "snac_updt_rhs": (C.c_int, [C.c_void_p]),
     "snac_fft": (C.c_int, [C.c_void_p, C.c_int]),

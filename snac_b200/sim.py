@@ -155,6 +155,17 @@ class Simulation:
     def boundp(self, field=L.FIELD_P):
         self._chk(self.lib.snac_boundp(self.h, field))
 
+    def set_inflow(self, planes):
+        """planes[r][(idir, ib)] = (veln, velt1, velt2) as returned by ``case.inflow_planes``
+        (u_in/v_in/w_in of the reference, src/main.f90:594-632)."""
+        for r in self.ranks:
+            for (idir, ib), vel in planes.get(r, {}).items():
+                a = [np.asfortranarray(v, dtype=np.float64) for v in vel]
+                self._chk(self.lib.snac_set_inflow(self.h, r, idir, ib, *[x.ctypes.data_as(C.c_void_p) for x in a]))
+
+    def inflow(self, is_correc):
+        self._chk(self.lib.snac_inflow(self.h, int(bool(is_correc))))
+
     def fillps(self, dtrk):
         self._chk(self.lib.snac_fillps(self.h, dtrk))
 
@@ -204,11 +215,12 @@ class Simulation:
 
     # -- driver logic (src/main.f90) -------------------------------------------------------------
     def init_bc(self):
-        """src/main.f90:562-568."""
+        """src/main.f90:562-568,633-635."""
         self.bounduvw(False)
         self.boundp(L.FIELD_P)
         for i in range(self.case.params.nscal):
             self.boundp(L.FIELD_S0 + i)
+        self.inflow(False)
 
     def set_dt(self):
         """src/main.f90:660-662,1051-1052."""

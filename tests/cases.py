@@ -57,7 +57,7 @@ def write_case(rundir, blocks, visci=100.0, cfl=0.95, dt_f=-1.0, icheck=10, hypr
             for c in range(3):
                 f.write(f"block_bcvel(0:1,1:3,{c + 1},{ib}) = {_f(bcv[c])}\n")
             f.write(f"block_bcpre(0:1,1:3,{ib}) = {_f(bcp)}\n")
-            f.write(f"block_inflow_type(0:1,1:3,{ib}) = 0, 0, 0, 0, 0, 0\n")
+            f.write(f"block_inflow_type(0:1,1:3,{ib}) = {', '.join(str(int(x)) for x in b.get('inflow_type', [0] * 6))}\n")
             f.write(f"block_inivel({ib}) = '{b.get('inivel', 'zer')}'\n\n")
         f.write("/\n")
 
@@ -102,13 +102,25 @@ def duct_blocks_case(rundir, n=(8, 8, 8), **kw):
     write_case(rundir, blocks, **kw)
 
 
+def developing_channel_case(rundir, ng=(16, 8, 12), dims=(2, 1, 2), inflow=1, **kw):
+    """The reference's examples/developing_channel topology (inflow at x-, outflow with p = 0 at x+, y periodic,
+    walls in z) with an inflow plane of the given type on x- (src/main.f90:594-632; 1 = Poiseuille)."""
+    bcv = [[0.0] * 6 for _ in range(3)]
+    bcv[0][0] = 1.0   # bulk velocity of the inflow profile
+    blk = dict(dims=dims, ng=ng, lmin=(0, 0, 0), lmax=(1.0, 1.5, 1.0), cbcvel=["DNFFDD", "NNFFDD", "NNFFDD"],
+               cbcpre="NDFFNN", bcvel=bcv, inflow_type=[inflow, 0, 0, 0, 0, 0], inivel="zer")
+    kw.setdefault("visci", 100.0)
+    write_case(rundir, [blk], **kw)
+
+
 def make(kind, rundir, fft_axis=0, impdiff=False, boussinesq=False, **kw):
     # the transform axis must not be decomposed (reference src/sanity.f90:75-79)
     if kind == "channel" and fft_axis == 1:
         kw.setdefault("dims", (1, 2, 2))
     if kind == "cavity" and fft_axis == 2:
         kw.setdefault("dims", (2, 1, 1))
-    {"channel": channel_case, "cavity": cavity_case, "tgv": tgv_case, "duct": duct_blocks_case}[kind](rundir, **kw)
+    {"channel": channel_case, "cavity": cavity_case, "tgv": tgv_case, "duct": duct_blocks_case,
+     "devchannel": developing_channel_case}[kind](rundir, **kw)
     return setup_case(rundir, fft_axis=fft_axis, impdiff=impdiff, boussinesq=boussinesq)
 
 

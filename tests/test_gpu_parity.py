@@ -286,6 +286,30 @@ def test_full_steps_match_oracle(tmp_path, kind, fa, kw):
     assert divmax < 1e-9
 
 
+@pytest.mark.parametrize("fa", [0, 2])
+def test_inflow_steps_match_oracle(tmp_path, fa):
+    """`inflow` (src/bound.f90:438-477) with a Poiseuille inflow plane (init_inflow, src/initflow.f90:369-429)
+    on the reference's developing-channel topology: planes set through snac_set_inflow, 8 steps vs. the oracle."""
+    from snac_b200.case import inflow_planes
+    case = cases.make("devchannel", str(tmp_path), fft_axis=fa)
+    flags, planes = inflow_planes(case)
+    assert any(f.any() for f in flags.values())
+    ini = initial_fields(case)
+    o, g = make_pair(case, ini, tol=1e-12, maxiter=200)
+    o.set_inflow([flags[r] for r in range(o.nr)], planes)
+    g.set_inflow(planes)
+    o.init_bc(); g.init_bc()
+    cmp_uvw(o, g, 1e-14)
+    o.set_dt(); g.set_dt()
+    assert abs(o.dt - g.dt) <= 1e-13 * o.dt
+    for _ in range(8):
+        o.step(); g.step()
+    assert max(np.abs(o.u[r]).max() for r in range(o.nr)) > 0.5   # the inflow drives the flow
+    cmp_uvw(o, g, 1e-8)
+    divtot, divmax = g.chkdiv()
+    assert divmax < 1e-9
+
+
 @pytest.mark.parametrize("fft_axis", [0, 1])
 def test_ldc_golden_vector_on_gpu(fft_axis):
     """The reference's own test (tests/lid_driven_cavity/test.py:5-16) run through the CUDA path:
