@@ -18,6 +18,7 @@
 #include <cmath>
 
 #include "common.h"
+#include "fft_radix.cuh"
 
 namespace snac {
 
@@ -115,6 +116,17 @@ static std::vector<double> dense_matrix(int kind, int N) {
   return M;
 }
 
+// twiddle tables of the fast kernels: m/2 complex e^{-2 pi i q/m} (m = n/2), then m/2+1 complex
+// e^{-2 pi i k/n}, then m+1 complex e^{-i pi k/(2n)}
+std::vector<double> r2r_fast_tables(int n) {
+  const int m = n / 2;
+  std::vector<double> t;
+  for (int k = 0; k < m / 2; ++k) { t.push_back(cospi_frac(2L * k, m)); t.push_back(-sinpi_frac(2L * k, m)); }
+  for (int k = 0; k <= m / 2; ++k) { t.push_back(cospi_frac(2L * k, n)); t.push_back(-sinpi_frac(2L * k, n)); }
+  for (int k = 0; k <= m; ++k) { t.push_back(cospi_frac(k, 2L * n)); t.push_back(-sinpi_frac(k, 2L * n)); }
+  return t;
+}
+
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
 void r2r_plan_init(R2RPlan &pl, int axis, int n, const char bc[2], bool centered) {
@@ -130,13 +142,7 @@ void r2r_plan_init(R2RPlan &pl, int axis, int n, const char bc[2], bool centered
   };
   pl.fast = (q == 0) && is_pow2(n) && n >= 8 && n <= 4096 && fast_kind(pl.kind_fwd) && fast_kind(pl.kind_bwd);
   if (pl.fast) {
-    // tables: [0, m) complex e^{-2 pi i q/m} (q < m/2 used), then n/4+1 complex e^{-2 pi i k/n},
-    // then m+1 complex e^{-i pi k/(2n)}
-    const int m = n / 2;
-    std::vector<double> t;
-    for (int k = 0; k < m / 2; ++k) { t.push_back(cospi_frac(2L * k, m)); t.push_back(-sinpi_frac(2L * k, m)); }
-    for (int k = 0; k <= m / 2; ++k) { t.push_back(cospi_frac(2L * k, n)); t.push_back(-sinpi_frac(2L * k, n)); }
-    for (int k = 0; k <= m; ++k) { t.push_back(cospi_frac(k, 2L * n)); t.push_back(-sinpi_frac(k, 2L * n)); }
+    const std::vector<double> t = r2r_fast_tables(n);
     pl.twiddle.upload(t);
   } else {
     if ((size_t)pl.nt * pl.nt > (size_t)1 << 24) throw Error("transform length too large for the generic path");
@@ -148,24 +154,6 @@ void r2r_plan_init(R2RPlan &pl, int axis, int n, const char bc[2], bool centered
 // ------------------------------------------------------------------------------------------
 // device
 // ------------------------------------------------------------------------------------------
-struct R2RArgs {
-  // first interior element of the input / output array; when the wavenumber axis of that side is
-  // split over processes (nsplit > 1), one base per owning process, chosen by index / chunk
-  const double *inp[16];
-  double *outp[16];
-  int in_split, out_split, chunk;
-  long ist[3], ost[3];  // strides of the physical directions x,y,z in the input / output arrays
-  int n[3];
-  int axis;
-  int nt;            // transform length
-  int tp;            // pencils per tile
-  int pd, od;        // direction along which a tile gathers pencils; the remaining direction
-  int kind;
-  int in_lane_t, out_lane_t;  // consecutive lanes walk along the transform axis (it has stride 1)
-  double scale;
-  const double *tab; // twiddles (fast) or dense matrix (generic)
-};
-
 // pencil p of tile `tile` -> offsets of its first element in the two arrays; false if out of range
 __device__ inline bool pencil_base(const R2RArgs &a, int tile, int p, long &ib, long &ob) {
   const int ntp = (a.n[a.pd] + a.tp - 1) / a.tp;
@@ -178,8 +166,6 @@ __device__ inline bool pencil_base(const R2RArgs &a, int tile, int p, long &ib, 
 }
 
 // iterate work items (p, t) with the lane-fastest index chosen for coalescing
-#define R2R_IN(t) (a.inp[a.in_split ? (t) / a.chunk : 0])
-#define R2R_OUT(t) (a.outp[a.out_split ? (t) / a.chunk : 0])
 
 #define FOR_ITEMS(LANE_T_, NT_, ...)                                                     \
   {                                                                                      \
@@ -381,6 +367,51 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
   }
 }
 
+// register-radix kernels (fft_radix.cuh): one CTA per tile of 16 pencils
+template <int R1, int R2, bool FWD>
+__global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS) r2r_radix_kernel(const R2RArgs a) {
+  extern __shared__ __align__(16) double2 Zs[];
+  const radix::Thread T = radix::thread_of(a, threadIdx.x, blockDim.x, blockIdx.x);
+  if (FWD) {
+    radix::fwd_pass1<R1, R2>(a, Zs, T);
+    __syncthreads();
+    radix::run_pass<R1, R2, false>(a, Zs, T);
+    __syncthreads();
+    radix::fwd_untangle<R1, R2>(a, Zs, T);
+  } else {
+    radix::bwd_tangle<R1, R2>(a, Zs, T);
+    __syncthreads();
+    radix::run_pass<R1, R2, true>(a, Zs, T);
+    __syncthreads();
+    radix::bwd_pass2<R1, R2>(a, Zs, T);
+  }
+}
+
+template <int R1, int R2>
+static void radix_go(cudaStream_t st, const R2RArgs &a, int dir, long ntiles) {
+  using P = radix::Plan<R1, R2>;
+  static bool attr = false;
+  if (!attr && P::SMEM > 48 * 1024) {
+    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+    attr = true;
+  }
+  if (dir > 0) r2r_radix_kernel<R1, R2, true><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
+  else r2r_radix_kernel<R1, R2, false><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
+}
+
+// transform lengths served by the radix kernels: n = 2 R1 R2
+static bool radix_launch(cudaStream_t st, const R2RArgs &a, int dir, long ntiles) {
+  switch (a.nt) {
+    case 32: radix_go<4, 4>(st, a, dir, ntiles); return true;
+    case 64: radix_go<8, 4>(st, a, dir, ntiles); return true;
+    case 128: radix_go<8, 8>(st, a, dir, ntiles); return true;
+    case 256: radix_go<16, 8>(st, a, dir, ntiles); return true;
+    case 512: radix_go<16, 16>(st, a, dir, ntiles); return true;
+    default: return false;
+  }
+}
+
 void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *const *in, int in_split,
                  const long ist[3], double *const *out, int out_split, const long ost[3], int chunk, double scale) {
   R2RArgs a;
@@ -405,6 +436,18 @@ void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const do
   a.tp = tp;
   const long ntiles = (long)((n3[a.pd] + tp - 1) / tp) * n3[a.od];
   const size_t smem = (size_t)n * (tp + 1) * sizeof(double);
+  static const bool staged_only = getenv("SNAC_FFT_STAGED") && atoi(getenv("SNAC_FFT_STAGED")) != 0;   // test hook
+  if (pl.fast && !a.in_lane_t && !a.out_lane_t && !staged_only) {
+    a.tab = pl.twiddle.p();
+    a.tp = radix::TP;
+    const long nt16 = (long)((n3[a.pd] + radix::TP - 1) / radix::TP) * n3[a.od];
+    if (radix_launch(ctx.stream, a, dir, nt16)) {
+      ctx.launches++;
+      SNAC_CUDA(cudaGetLastError());
+      return;
+    }
+    a.tp = tp;
+  }
   if (pl.fast) {
     a.tab = pl.twiddle.p();
     if (dir > 0) {

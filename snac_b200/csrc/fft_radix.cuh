@@ -1,0 +1,333 @@
+// K3b/K5, register-radix form of the fast real-to-real transforms (included by fft.cu).
+//
+// Same mathematics as r2r_fast_kernel (a real transform of length n as one complex transform of
+// length m = n/2 plus an untangling step; DCT/DST-II/III through Makhoul's even/odd permutation and
+// a post/pre-twiddle), different data movement: the complex transform is done in two in-place
+// mixed-radix passes, m = R1 * R2 with radices up to 16 held in registers,
+//
+//   forward :  global -> [radix-R1 butterflies at stride m/R1, twiddle] -> smem
+//              smem   -> [radix-R2 butterflies on contiguous runs]      -> smem   (digit-reversed)
+//              smem   -> untangle + post-twiddle                        -> global
+//   backward:  global -> pre-twiddle + inverse untangle                 -> smem   (digit-reversed)
+//              smem   -> [radix-R2 on contiguous runs, twiddle]         -> smem
+//              smem   -> [radix-R1 at stride m/R1]                      -> global
+//
+// so that (i) every thread has all the global loads of its butterfly (2 R1 rows) in flight at once --
+// the staged kernel issued them one by one in front of a shared-memory store and was bound by that
+// latency -- and (ii) an element crosses shared memory twice instead of eight times.  Consecutive
+// lanes hold consecutive pencils (the unit-stride direction of both arrays), a complex element is
+// one 16-byte shared-memory word.  Used when neither side has the transform axis at unit stride
+// (FFT_AXIS = 2, 3); otherwise the staged kernel does the transposition through shared memory.
+//
+// The phase functions are __host__ __device__ so that tests/host/fft_emul.cu can run them thread by
+// thread on the CPU against the dense transform definitions (no GPU needed for the index algebra).
+#pragma once
+#include "common.h"
+
+namespace snac {
+
+struct R2RArgs {
+  // first interior element of the input / output array; when the wavenumber axis of that side is
+  // split over processes (nsplit > 1), one base per owning process, chosen by index / chunk
+  const double *inp[16];
+  double *outp[16];
+  int in_split, out_split, chunk;
+  long ist[3], ost[3];  // strides of the physical directions x,y,z in the input / output arrays
+  int n[3];
+  int axis;
+  int nt;            // transform length
+  int tp;            // pencils per tile
+  int pd, od;        // direction along which a tile gathers pencils; the remaining direction
+  int kind;
+  int in_lane_t, out_lane_t;  // consecutive lanes walk along the transform axis (it has stride 1)
+  double scale;
+  const double *tab; // twiddles (fast) or dense matrix (generic)
+};
+
+#define R2R_IN(t) (a.inp[a.in_split ? (t) / a.chunk : 0])
+#define R2R_OUT(t) (a.outp[a.out_split ? (t) / a.chunk : 0])
+
+#if defined(__CUDA_ARCH__)
+#define SNAC_LDG(p) __ldg(p)
+#else
+#define SNAC_LDG(p) (*(p))
+#endif
+#define SNAC_HD __host__ __device__ __forceinline__
+
+namespace radix {
+
+struct Cx { double x, y; };
+SNAC_HD Cx operator+(Cx a, Cx b) { return {a.x + b.x, a.y + b.y}; }
+SNAC_HD Cx operator-(Cx a, Cx b) { return {a.x - b.x, a.y - b.y}; }
+SNAC_HD Cx cmul(Cx a, Cx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+
+// cos(2 pi k / 16), sin(2 pi k / 16), k = 0..15
+#define SNAC_C16 {1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173, 0.0, -0.38268343236508977173, \
+                  -0.70710678118654752440, -0.92387953251128673848, -1.0, -0.92387953251128673848, -0.70710678118654752440, \
+                  -0.38268343236508977173, 0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848}
+#define SNAC_S16 {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848, 1.0, 0.92387953251128673848, \
+                  0.70710678118654752440, 0.38268343236508977173, 0.0, -0.38268343236508977173, -0.70710678118654752440, \
+                  -0.92387953251128673848, -1.0, -0.92387953251128673848, -0.70710678118654752440, -0.38268343236508977173}
+
+// v *= exp(-/+ 2 pi i K / 16) (INV: +), K a compile-time constant after unrolling
+template <bool INV>
+SNAC_HD Cx rot16(Cx v, int K) {
+  constexpr double c16[16] = SNAC_C16, s16[16] = SNAC_S16;
+  K &= 15;
+  if (K == 0) return v;
+  if (K == 4) return INV ? Cx{-v.y, v.x} : Cx{v.y, -v.x};
+  if (K == 8) return Cx{-v.x, -v.y};
+  if (K == 12) return INV ? Cx{v.y, -v.x} : Cx{-v.y, v.x};
+  const double c = c16[K], s = INV ? s16[K] : -s16[K];
+  return Cx{v.x * c - v.y * s, v.x * s + v.y * c};
+}
+
+__host__ __device__ constexpr int brev_c(int k, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; ++b) r |= ((k >> b) & 1) << (bits - 1 - b);
+  return r;
+}
+__host__ __device__ constexpr int log2_c(int n) { return n <= 1 ? 0 : 1 + log2_c(n / 2); }
+
+// unnormalised DFT of length R (a power of two <= 16) in registers, natural order in and out:
+//   v[k] <- sum_j v[j] exp(-/+ 2 pi i j k / R)
+template <int R, bool INV>
+SNAC_HD void dft(Cx (&v)[R]) {
+#pragma unroll
+  for (int len = R; len >= 2; len >>= 1) {   // radix-2 DIF stages: natural -> bit-reversed
+    const int half = len >> 1;
+#pragma unroll
+    for (int b = 0; b < R; b += len) {
+#pragma unroll
+      for (int t = 0; t < half; ++t) {
+        const Cx p = v[b + t], q = v[b + t + half];
+        v[b + t] = p + q;
+        v[b + t + half] = rot16<INV>(p - q, t * (16 / len));
+      }
+    }
+  }
+  constexpr int bits = log2_c(R);
+#pragma unroll
+  for (int k = 0; k < R; ++k) {   // undo the bit reversal (register renaming after unrolling)
+    const int r = brev_c(k, bits);
+    if (r > k) { const Cx t = v[k]; v[k] = v[r]; v[r] = t; }
+  }
+}
+
+constexpr int TP = 16;   // pencils per tile = lanes along the unit-stride direction
+
+// per-thread constants of a tile
+struct Thread {
+  int p, jt, tpp;      // pencil in the tile, index among the threads of that pencil, threads per pencil
+  bool valid;          // the pencil exists
+  long ib, ob;         // offsets of the pencil's first element in the input / output arrays
+};
+
+SNAC_HD Thread thread_of(const R2RArgs &a, int tid, int nthr, int tile) {
+  Thread T;
+  T.p = tid % TP; T.jt = tid / TP; T.tpp = nthr / TP;
+  const int ntp = (a.n[a.pd] + TP - 1) / TP;
+  const int tpi = tile % ntp, o = tile / ntp;
+  const int ip = tpi * TP + T.p;
+  T.valid = ip < a.n[a.pd];
+  T.ib = ip * a.ist[a.pd] + o * a.ist[a.od];
+  T.ob = ip * a.ost[a.pd] + o * a.ost[a.od];
+  return T;
+}
+
+// e^{-2 pi i k / m} for 0 <= k < m from the table of the first half turn
+SNAC_HD Cx tw_m(const double *tw, int k, int m) {
+  const int h = m >> 1;
+  const int kk = k >= h ? k - h : k;
+  Cx w{SNAC_LDG(tw + 2 * kk), SNAC_LDG(tw + 2 * kk + 1)};
+  if (k >= h) { w.x = -w.x; w.y = -w.y; }
+  return w;
+}
+
+// Makhoul's permutation: slot s of the permuted sequence holds input element tof(s)
+SNAC_HD int tof(int s, int n, bool makhoul) { return !makhoul ? s : (2 * s < n ? 2 * s : 2 * (n - 1 - s) + 1); }
+
+template <int R1, int R2>
+struct Plan {
+  static constexpr int M = R1 * R2;       // complex length
+  static constexpr int N = 2 * M;         // real length
+  static constexpr int S1 = R2;           // stride of the first pass = length of the contiguous runs
+  static constexpr int TPP = R1 < R2 ? R1 : R2;   // threads per pencil
+  static constexpr int THREADS = TP * TPP;
+  static constexpr size_t SMEM = (size_t)M * TP * sizeof(double2);
+  SNAC_HD static int loc(int k) { return (k % R1) * S1 + k / R1; }   // where X[k] sits after the two passes
+};
+
+SNAC_HD bool is_makhoul(int kind) { return kind == K_REDFT10 || kind == K_RODFT10 || kind == K_REDFT01 || kind == K_RODFT01; }
+SNAC_HD bool is_sine(int kind) { return kind == K_RODFT10 || kind == K_RODFT01; }
+
+// ---- forward ---------------------------------------------------------------------------------
+template <int R1, int R2>
+SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
+  using P = Plan<R1, R2>;
+  if (!T.valid) return;
+  const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
+  const long isa = a.ist[a.axis];
+  const double *tw = a.tab;
+  for (int j = T.jt; j < P::S1; j += T.tpp) {
+    Cx v[R1];
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      const int e = j + r * P::S1;
+      const int t0 = tof(2 * e, P::N, makhoul), t1 = tof(2 * e + 1, P::N, makhoul);
+      double x0 = R2R_IN(t0)[T.ib + t0 * isa], x1 = R2R_IN(t1)[T.ib + t1 * isa];
+      if (sine && (t0 & 1)) x0 = -x0;
+      if (sine && (t1 & 1)) x1 = -x1;
+      v[r] = Cx{x0, x1};
+    }
+    dft<R1, false>(v);
+#pragma unroll
+    for (int q = 0; q < R1; ++q) {
+      const Cx y = q == 0 ? v[0] : cmul(v[q], tw_m(tw, j * q, P::M));
+      Z[(j + q * P::S1) * TP + T.p] = make_double2(y.x, y.y);
+    }
+  }
+}
+
+template <int R1, int R2, bool INV>
+SNAC_HD void run_pass(const R2RArgs &a, double2 *Z, const Thread &T) {   // radix R2 on the contiguous runs
+  using P = Plan<R1, R2>;
+  if (!T.valid) return;
+  const double *tw = a.tab;
+  for (int q = T.jt; q < R1; q += T.tpp) {
+    Cx v[R2];
+#pragma unroll
+    for (int r = 0; r < R2; ++r) {
+      const double2 z = Z[(q * P::S1 + r) * TP + T.p];
+      v[r] = Cx{z.x, z.y};
+    }
+    dft<R2, INV>(v);
+#pragma unroll
+    for (int s = 0; s < R2; ++s) {
+      Cx y = v[s];
+      if (INV && s > 0 && q > 0) {   // backward: twiddle between the passes, conjugated
+        Cx w = tw_m(tw, s * q, P::M);
+        w.y = -w.y;
+        y = cmul(y, w);
+      }
+      Z[(q * P::S1 + s) * TP + T.p] = make_double2(y.x, y.y);
+    }
+  }
+}
+
+template <int R1, int R2>
+SNAC_HD void fwd_untangle(const R2RArgs &a, const double2 *Z, const Thread &T) {
+  using P = Plan<R1, R2>;
+  if (!T.valid) return;
+  constexpr int m = P::M, n = P::N, nk = m / 2 + 1;
+  const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
+  const long osa = a.ost[a.axis], ob = T.ob;
+  const double *wn = a.tab + 2 * (m / 2);   // e^{-2 pi i k/n}, k <= m/2
+  const double *wd = wn + 2 * (m / 2 + 1);  // e^{-i pi k/(2n)}, k <= m
+  const double sc = a.scale;
+  for (int k = T.jt; k < nk; k += T.tpp) {
+    const double2 zk2 = Z[P::loc(k) * TP + T.p], zm2 = Z[P::loc((m - k) & (m - 1)) * TP + T.p];
+    const Cx zk{zk2.x, zk2.y}, zm{zm2.x, zm2.y};
+    const Cx e{0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y)};
+    const Cx o{0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x)};   // -i/2 (zk - conj zm)
+    const Cx w{SNAC_LDG(wn + 2 * k), SNAC_LDG(wn + 2 * k + 1)};
+    const Cx wo = cmul(w, o);
+    const Cx xk{e.x + wo.x, e.y + wo.y};        // X[k]
+    const Cx xmk{e.x - wo.x, -(e.y - wo.y)};    // X[m-k]
+    const int ka = k, kb = m - k;               // the two output wavenumbers (k=0: 0 and m)
+#define SNAC_OUT_AT(idx) R2R_OUT(idx)[ob + (idx) * osa]
+    if (!makhoul) {
+      SNAC_OUT_AT(ka) = sc * xk.x;
+      if (k > 0) SNAC_OUT_AT(n - ka) = sc * xk.y;
+      SNAC_OUT_AT(kb) = sc * xmk.x;
+      if (k > 0 && kb < m) SNAC_OUT_AT(n - kb) = sc * xmk.y;
+    } else {
+      // X_c[k] = 2 Re(e^{-i pi k/2n} V[k]), X_c[n-k] = -2 Im(e^{-i pi k/2n} V[k])
+      {
+        const double c = SNAC_LDG(wd + 2 * ka), s_ = -SNAC_LDG(wd + 2 * ka + 1);
+        const double v0 = 2.0 * (c * xk.x + s_ * xk.y), v1 = 2.0 * (s_ * xk.x - c * xk.y);
+        const int o0 = sine ? (n - 1 - ka) : ka;
+        SNAC_OUT_AT(o0) = sc * v0;
+        if (ka > 0) { const int o1 = sine ? (ka - 1) : (n - ka); SNAC_OUT_AT(o1) = sc * v1; }
+      }
+      {
+        const double c = SNAC_LDG(wd + 2 * kb), s_ = -SNAC_LDG(wd + 2 * kb + 1);
+        const double v0 = 2.0 * (c * xmk.x + s_ * xmk.y), v1 = 2.0 * (s_ * xmk.x - c * xmk.y);
+        const int o0 = sine ? (n - 1 - kb) : kb;
+        SNAC_OUT_AT(o0) = sc * v0;
+        if (kb < m) { const int o1 = sine ? (kb - 1) : (n - kb); SNAC_OUT_AT(o1) = sc * v1; }
+      }
+    }
+#undef SNAC_OUT_AT
+  }
+}
+
+// ---- backward --------------------------------------------------------------------------------
+template <int R1, int R2>
+SNAC_HD void bwd_tangle(const R2RArgs &a, double2 *Z, const Thread &T) {
+  using P = Plan<R1, R2>;
+  if (!T.valid) return;
+  constexpr int m = P::M, n = P::N, nk = m / 2 + 1;
+  const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
+  const long isa = a.ist[a.axis], ib = T.ib;
+  const double *wn = a.tab + 2 * (m / 2);
+  const double *wd = wn + 2 * (m / 2 + 1);
+  for (int k = T.jt; k < nk; k += T.tpp) {
+#define SNAC_IN_AT(idx) R2R_IN(idx)[ib + (idx) * isa]
+    const int kb = m - k;
+    Cx xk, xm;  // X[k], X[m-k]
+    if (!makhoul) {
+      xk.x = SNAC_IN_AT(k);  xk.y = (k > 0) ? SNAC_IN_AT(n - k) : 0.0;
+      xm.x = SNAC_IN_AT(kb); xm.y = (kb < m) ? SNAC_IN_AT(n - kb) : 0.0;
+    } else {
+      auto getx = [&](int kk) -> Cx {
+        const double c = SNAC_LDG(wd + 2 * kk), s_ = -SNAC_LDG(wd + 2 * kk + 1);
+        const int i0 = sine ? (n - 1 - kk) : kk;
+        const double a0 = SNAC_IN_AT(i0);
+        double a1 = 0.0;
+        if (kk > 0) { const int i1 = sine ? (kk - 1) : (n - kk); a1 = SNAC_IN_AT(i1); }
+        return Cx{c * a0 + s_ * a1, s_ * a0 - c * a1};
+      };
+      xk = getx(k);
+      xm = getx(kb);
+    }
+#undef SNAC_IN_AT
+    // Z[k] = (X[k] + conj X[m-k]) + i e^{+2 pi i k/n} (X[k] - conj X[m-k])
+    const Cx w{SNAC_LDG(wn + 2 * k), -SNAC_LDG(wn + 2 * k + 1)};
+    const Cx sum{xk.x + xm.x, xk.y - xm.y}, dif{xk.x - xm.x, xk.y + xm.y};
+    const Cx wd_ = cmul(w, dif);
+    Z[P::loc(k & (m - 1)) * TP + T.p] = make_double2(sum.x - wd_.y, sum.y + wd_.x);
+    if (k > 0 && k != kb)   // Z[m-k] = conj( (X[k] + conj X[m-k]) - i e^{+2 pi i k/n}(X[k] - conj X[m-k]) )
+      Z[P::loc(kb) * TP + T.p] = make_double2(sum.x + wd_.y, -(sum.y - wd_.x));
+  }
+}
+
+template <int R1, int R2>
+SNAC_HD void bwd_pass2(const R2RArgs &a, const double2 *Z, const Thread &T) {   // radix R1 at stride S1, then the store
+  using P = Plan<R1, R2>;
+  if (!T.valid) return;
+  const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
+  const long osa = a.ost[a.axis];
+  for (int j = T.jt; j < P::S1; j += T.tpp) {
+    Cx v[R1];
+#pragma unroll
+    for (int q = 0; q < R1; ++q) {
+      const double2 z = Z[(q * P::S1 + j) * TP + T.p];
+      v[q] = Cx{z.x, z.y};
+    }
+    dft<R1, true>(v);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      const int e = j + r * P::S1;
+      const int t0 = tof(2 * e, P::N, makhoul), t1 = tof(2 * e + 1, P::N, makhoul);
+      double x0 = v[r].x * a.scale, x1 = v[r].y * a.scale;
+      if (sine && (t0 & 1)) x0 = -x0;
+      if (sine && (t1 & 1)) x1 = -x1;
+      R2R_OUT(t0)[T.ob + t0 * osa] = x0;
+      R2R_OUT(t1)[T.ob + t1 * osa] = x1;
+    }
+  }
+}
+
+}  // namespace radix
+}  // namespace snac

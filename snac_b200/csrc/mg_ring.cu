@@ -38,19 +38,20 @@ namespace snac {
 namespace {
 constexpr int RW = 64;    // columns per warp
 #ifndef SNAC_RING_RD
-#define SNAC_RING_RD 10
+#define SNAC_RING_RD 8
 #endif
 #ifndef SNAC_RING_RPD
-#define SNAC_RING_RPD 4
+#define SNAC_RING_RPD 2
 #endif
-// ring slots = window slots = unroll period of the march, down kernel: 10 slots x 136 doubles x 4 warps
-// = 43.5 KB per CTA, so that five CTAs (20 warps) fit on an SM (12 slots: four)
+// ring slots = window slots = unroll period of the march, down kernel.  Measured on TGV-256 (B200, same
+// box): 12 slots / 6 rows ahead (4 CTAs per SM) 2.37 ms per step, 10 / 4 (5 CTAs) 1.76-1.86 ms, 8 / 2
+// (5 CTAs, shorter unrolled body) 1.68 ms; 8 / 2 squeezed into 80 registers for 6 CTAs: 2.02 ms.
 constexpr int RD = SNAC_RING_RD;
 #ifndef SNAC_RING_RDU
 #define SNAC_RING_RDU 8
 #endif
 #ifndef SNAC_RING_MINB_D
-#define SNAC_RING_MINB_D 1
+#define SNAC_RING_MINB_D 5
 #endif
 #ifndef SNAC_RING_MINB_U
 #define SNAC_RING_MINB_U 1

@@ -107,9 +107,9 @@ def test_bound_rkmom_fillps_correc(tmp_path, kind, fa):
     assert abs(dt_g - dt_o) <= 1e-12 * max(abs(dt_o), 1.0)
 
 
-def _write_bc_case(tmp, n, axis, bc01):
+def _write_bc_case(tmp, n, axis, bc01, ng=(6, 5, 4)):
     """single block whose pressure BC pair along `axis` is bc01; other directions periodic."""
-    ng = [6, 5, 4]
+    ng = list(ng)
     ng[axis] = n
     pre = ["F"] * 6
     pre[2 * axis], pre[2 * axis + 1] = bc01[0], bc01[1]
@@ -148,6 +148,31 @@ def test_transforms_match_fftw_definitions(tmp_path, n, axis, bc01):
     g.fft(-1)
     back = g.download(0, L.FIELD_PP)
     assert rel(back[I], x[I]) < 1e-13 * max(1, np.log2(n))
+
+
+@pytest.mark.parametrize("n", [32, 128, 256, 512])
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("bc01", ["FF", "NN", "DD"])
+def test_long_transforms_match_fftw_definitions(tmp_path, n, axis, bc01):
+    """the benchmark lengths: register-radix kernels (axes y, z; tiles of 16 pencils, the last one partial)
+    and the staged kernel (axis x), forward against scipy.fft and the round trip."""
+    case = _write_bc_case(str(tmp_path), n, axis, bc01, ng=(37, 18, 3))
+    from snac_b200.sim import Simulation
+    g = Simulation(case)
+    plan = orc.FFTPlan(axis, n, bc01, True)
+    rng = np.random.default_rng(12)
+    x = np.asfortranarray(rng.standard_normal(g.shape(0)))
+    g.upload(0, L.FIELD_RHS, x)
+    g.fft(+1)
+    got = g.download(0, L.FIELD_RHS_HAT)
+    ref = x.copy(order="F")
+    plan.apply(ref[1:-1, 1:-1, 1:-1], 1)
+    I = (slice(1, -1),) * 3
+    assert rel(got[I], ref[I]) < 1e-13 * np.log2(n)
+    g.upload(0, L.FIELD_PO, got)
+    g.fft(-1)
+    back = g.download(0, L.FIELD_PP)
+    assert rel(back[I], x[I]) < 1e-13 * np.log2(n)
 
 
 # (kind, fft_axis, extra case arguments, force the general multi-box kernels)
