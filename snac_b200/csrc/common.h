@@ -274,6 +274,7 @@ struct CoarseArgs {
   double *norms;             // only when the top level is level 0
   double xscale;             // factor applied to xin
   int nq, want_b, npre, npost, nbot;
+  int adaptive;              // per-wavenumber depth of the hierarchy (mg_coarse.cu)
   const int *active;
 };
 size_t mg_coarse_smem(const CoarseArgs &a, bool single);

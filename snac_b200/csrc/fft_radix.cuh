@@ -169,7 +169,10 @@ SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
   const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
   const long isa = a.ist[a.axis];
   const double *tw = a.tab;
-  for (int j = T.jt; j < P::S1; j += T.tpp) {
+#pragma unroll
+  for (int j0 = 0; j0 < P::S1; j0 += P::TPP) {
+    const int j = j0 + T.jt;
+    if (j >= P::S1) break;
     Cx v[R1];
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
@@ -194,7 +197,10 @@ SNAC_HD void run_pass(const R2RArgs &a, double2 *Z, const Thread &T) {   // radi
   using P = Plan<R1, R2>;
   if (!T.valid) return;
   const double *tw = a.tab;
-  for (int q = T.jt; q < R1; q += T.tpp) {
+#pragma unroll
+  for (int q0 = 0; q0 < R1; q0 += P::TPP) {
+    const int q = q0 + T.jt;
+    if (q >= R1) break;
     Cx v[R2];
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
@@ -225,7 +231,10 @@ SNAC_HD void fwd_untangle(const R2RArgs &a, const double2 *Z, const Thread &T) {
   const double *wn = a.tab + 2 * (m / 2);   // e^{-2 pi i k/n}, k <= m/2
   const double *wd = wn + 2 * (m / 2 + 1);  // e^{-i pi k/(2n)}, k <= m
   const double sc = a.scale;
-  for (int k = T.jt; k < nk; k += T.tpp) {
+#pragma unroll
+  for (int k0 = 0; k0 < nk; k0 += P::TPP) {
+    const int k = k0 + T.jt;
+    if (k >= nk) break;
     const double2 zk2 = Z[P::loc(k) * TP + T.p], zm2 = Z[P::loc((m - k) & (m - 1)) * TP + T.p];
     const Cx zk{zk2.x, zk2.y}, zm{zm2.x, zm2.y};
     const Cx e{0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y)};
@@ -272,7 +281,10 @@ SNAC_HD void bwd_tangle(const R2RArgs &a, double2 *Z, const Thread &T) {
   const long isa = a.ist[a.axis], ib = T.ib;
   const double *wn = a.tab + 2 * (m / 2);
   const double *wd = wn + 2 * (m / 2 + 1);
-  for (int k = T.jt; k < nk; k += T.tpp) {
+#pragma unroll
+  for (int k0 = 0; k0 < nk; k0 += P::TPP) {
+    const int k = k0 + T.jt;
+    if (k >= nk) break;
 #define SNAC_IN_AT(idx) R2R_IN(idx)[ib + (idx) * isa]
     const int kb = m - k;
     Cx xk, xm;  // X[k], X[m-k]
@@ -308,7 +320,10 @@ SNAC_HD void bwd_pass2(const R2RArgs &a, const double2 *Z, const Thread &T) {   
   if (!T.valid) return;
   const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
   const long osa = a.ost[a.axis];
-  for (int j = T.jt; j < P::S1; j += T.tpp) {
+#pragma unroll
+  for (int j0 = 0; j0 < P::S1; j0 += P::TPP) {
+    const int j = j0 + T.jt;
+    if (j >= P::S1) break;
     Cx v[R1];
 #pragma unroll
     for (int q = 0; q < R1; ++q) {

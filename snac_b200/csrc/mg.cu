@@ -1308,6 +1308,18 @@ struct Cycle {
       a.xscale = (ls == 0 && want_b) ? S.guess_scale : 1.0;
       a.nq = S.nq; a.want_b = want_b ? 1 : 0;
       a.npre = npre; a.npost = npost; a.nbot = nbot;
+      {
+        static const bool adapt = !(getenv("SNAC_MG_COARSE_ADAPT") && atoi(getenv("SNAC_MG_COARSE_ADAPT")) == 0);
+        a.adaptive = (ls > 0 && adapt) ? 1 : 0;
+      }
+      if (ls > 0) {   // tuning hooks for the FP32 coarse-grid correction: sweeps per leg, depth of the hierarchy
+        static const int csw = getenv("SNAC_MG_COARSE_NSW") ? atoi(getenv("SNAC_MG_COARSE_NSW")) : 0;
+        static const int cml = getenv("SNAC_MG_COARSE_MAXLEV") ? atoi(getenv("SNAC_MG_COARSE_MAXLEV")) : 0;
+        static const int cnb = getenv("SNAC_MG_COARSE_NBOT") ? atoi(getenv("SNAC_MG_COARSE_NBOT")) : 0;
+        if (csw > 0) a.npre = a.npost = csw;
+        if (cml > 0) a.nlev = std::min(a.nlev, cml);
+        if (cnb > 0) a.nbot = cnb;
+      }
       a.active = S.d_active;
       launch_mg_coarse(ctx.stream, a, S.coarse_single);
       ctx.launches++;

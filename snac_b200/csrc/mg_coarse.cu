@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   const int q = blockIdx.x;
   if (a.active && !a.active[q]) return;
   const T lam = (T)(a.alpha + __ldg(a.lamq + q + 1));
-  const int nlev = a.nlev;
+  int nlev = a.nlev;
+  __shared__ int s_nlev, s_nbot;
   const CGroup GB{(int)threadIdx.x, (int)blockDim.x, false}, GW{(int)threadIdx.x, 32, true};
   if (threadIdx.x == 0) {   // carve the shared memory
     int p = 0;
@@ -189,9 +190,6 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
     }
   }
   __syncthreads();
-  // first level left to warp 0 alone (at most 256 cells); level 0 always belongs to the CTA
-  int lsw = nlev;
-  while (lsw > 1 && lv[lsw - 1].n1 * lv[lsw - 1].n2 <= 256) --lsw;
   // coefficient tables (global tables are 1-based with 8 doubles per entry: na_m, na_p, e, w, 1/w)
   for (int l = 0; l < nlev; ++l) {
     const CLev L = lv[l];
@@ -209,6 +207,32 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
         t[3 * n + i] = (gc && co) ? (T)(w / __ldg(gc + 8 * ((i >> 1) + 1) + 3)) : (T)1;
       }
     }
+  }
+  // Depth of the hierarchy for THIS wavenumber: on a level where the shift lambda dominates the
+  // diagonal, lambda >= r (e1 + e2) with r >= 1/2, Gauss-Seidel itself contracts by about
+  // 1/(1+r)^2 per sweep, so that level is solved by a few sweeps and the levels below it (the
+  // latency-bound tail of the cycle, run by one warp) are not visited.  Planes with a small shift
+  // (the low wavenumbers, lambda -> 0) keep the whole hierarchy.
+  if (a.adaptive && nlev > 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int nl = nlev, nb = a.nbot;
+      for (int l = 1; l < nlev; ++l) {
+        const CLev L = lv[l];
+        const double e = (double)sm[L.o1 + 2 * L.n1 + L.n1 / 2] + (double)sm[L.o2 + 2 * L.n2 + L.n2 / 2];
+        const double r = e != 0.0 ? (double)lam / e : 0.0;   // > 0: the shift has the sign of the diagonal
+        if (r >= 0.5) {
+          nl = l + 1;
+          nb = min(a.nbot, (int)ceil(4.6 / log1p(r)));   // (1+r)^(-2 nb) <= 1e-4
+          break;
+        }
+      }
+      s_nlev = nl; s_nbot = nb;
+    }
+    __syncthreads();
+    nlev = s_nlev;
+  } else if (threadIdx.x == 0) {
+    s_nbot = a.nbot;
   }
   // top level: right-hand side (scaled) and iterate; rows of the plane are contiguous in memory
   {
@@ -228,6 +252,10 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
     }
   }
   __syncthreads();
+  const int nbot = s_nbot;
+  // first level left to warp 0 alone (at most 256 cells); level 0 always belongs to the CTA
+  int lsw = nlev;
+  while (lsw > 1 && lv[lsw - 1].n1 * lv[lsw - 1].n2 <= 256) --lsw;
   double r2 = 0.0, b2 = 0.0;
   // ---- down leg, CTA-wide levels
   for (int l = 0; l < lsw - 1; ++l) {
@@ -247,7 +275,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
         c_down(sm, F, C, lam, a.npre, GW, false, r2, b2);
       }
       const CLev B = lv[nlev - 1];
-      const int ns = min(a.nbot, B.n1 * B.n2);   // a 1 x 1 level is solved by one update
+      const int ns = min(nbot, B.n1 * B.n2);   // a 1 x 1 level is solved by one update
       for (int s = 0; s < ns; ++s) { c_sweep(sm, B, 0, lam, GW); c_sweep(sm, B, 1, lam, GW); }
       for (int l = nlev - 2; l >= lsw; --l) {
         const CLev F = lv[l], C = lv[l + 1];
@@ -261,7 +289,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
     }
   } else {   // the coarsest level belongs to the CTA (a single-level or all-large hierarchy)
     const CLev B = lv[nlev - 1];
-    const int ns = min(a.nbot, B.n1 * B.n2);
+    const int ns = min(nbot, B.n1 * B.n2);
     for (int s = 0; s < ns; ++s) { c_sweep(sm, B, 0, lam, GB); c_sweep(sm, B, 1, lam, GB); }
     if (nlev == 1 && a.norms) {
       for (int t = threadIdx.x; t < B.n1 * B.n2; t += blockDim.x) {

@@ -21,8 +21,11 @@ struct MomArgs {
   double gb[3];      // gacc*beta
 };
 
+#ifndef SNAC_MOM_MINB
+#define SNAC_MOM_MINB 3
+#endif
 template <bool IMPDIFF, bool BUOY, bool FIRST>
-__global__ void __launch_bounds__(256) rk_mom_kernel(const MomArgs a) {
+__global__ void __launch_bounds__(256, SNAC_MOM_MINB) rk_mom_kernel(const MomArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   const int k = blockIdx.z * blockDim.z + threadIdx.z + 1;
