@@ -745,6 +745,7 @@ static void substep(Ctx &ctx, int irk, double dt) {
     ctx.psolver.guess_scale = (on && ctx.psolver.plane_local && ctx.prev_dtrk > 0.0) ? dtrk / ctx.prev_dtrk : 1.0;
     ctx.prev_dtrk = dtrk;
   }
+  ctx.psolver.hist_key = irk - 1;   // the three pressure solves of a step behave differently, each like its predecessor a step earlier
   if (ctx.prm.fft_axis > 0) {
     do_fft(ctx, +1);
     do_solve(ctx);

@@ -332,7 +332,15 @@ struct MGSolver {
   bool coarse_old = false;         // A/B switch: the previous shared-memory kernel
   std::vector<Field3> x1;          // second x buffer of the tiled levels [level*nbox + box]
   int *d_active = nullptr, *d_where = nullptr, *d_iters = nullptr, *d_count = nullptr;  // per-plane stopping flags
-  int *h_count = nullptr;          // pinned
+  int *h_count = nullptr;          // pinned: [0] the polled counter, then the histories below
+  // planes still iterating after every cycle of the last solve, per caller-chosen key (the sub-step):
+  // consecutive time steps behave alike, so the record of the previous solve sizes the launches of
+  // this one cycle by cycle and tells how many cycles to enqueue before the first poll
+  static constexpr int HIST_KEYS = 4, HIST_LEN = 64;
+  int hist_key = 0;
+  int hist_cur[HIST_KEYS] = {0, 0, 0, 0};   // which of the two records of a key is being written
+  int hist_n[HIST_KEYS] = {0, 0, 0, 0};     // cycles in the complete record (0: none yet)
+  int *hist(int key, int which) const { return h_count + 16 + ((key * 2 + which) * HIST_LEN); }
   double last_mean_iters = 0.0;
   int est_active = 0;              // planes still iterating at the last poll (sizes the work items of the next launches)
   void stats(Ctx &ctx, int *iters, double *relres, double *mean_iters);

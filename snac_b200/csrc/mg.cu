@@ -926,7 +926,8 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
     SNAC_CUDA(cudaMalloc(&d_active, (3 * (size_t)nq + 4) * sizeof(int)));
     d_where = d_active + nq; d_iters = d_where + nq; d_count = d_iters + nq;
     SNAC_CUDA(cudaMemset(d_active, 0, (3 * (size_t)nq + 4) * sizeof(int)));
-    SNAC_CUDA(cudaMallocHost(&h_count, sizeof(int)));
+    SNAC_CUDA(cudaMallocHost(&h_count, (16 + 2 * HIST_KEYS * HIST_LEN) * sizeof(int)));
+    for (int i = 0; i < 16 + 2 * HIST_KEYS * HIST_LEN; ++i) h_count[i] = 0;
   }
   lam.clear();
   lam.resize(nl);
@@ -1388,10 +1389,25 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
   mg_flags_init_kernel<<<1, 256, 0, ctx.stream>>>(S.d_active, S.d_where, S.d_iters, S.d_count, nq);
   ctx.launches++;
   int it = 0;
-  S.est_active = nq;
+  // record of the last solve with the same key (see MGSolver::hist)
+  static const bool use_hist = !(getenv("SNAC_MG_HISTORY") && atoi(getenv("SNAC_MG_HISTORY")) == 0);
+  const int key = S.hist_key & (MGSolver::HIST_KEYS - 1);
+  const int *prev = S.hist(key, 1 - S.hist_cur[key]);
+  int *cur = S.hist(key, S.hist_cur[key]);
+  const int prev_n = use_hist ? S.hist_n[key] : 0;
+  int polled = nq;
+  auto predict = [&](int i) -> int {   // planes still iterating after cycle i
+    if (i < 0) return nq;
+    if (i < prev_n) return std::min(nq, std::max(1, prev[i] + prev[i] / 8 + 1));
+    return std::max(1, polled);
+  };
+  bool first = true;
   for (;;) {
-    const int batch = 3;
+    // cycles enqueued before the host looks at the counter: as many as the last solve needed, then two at a time
+    const int batch = first ? (prev_n > 0 ? std::min(prev_n, maxiter + 1) : 3) : 2;
+    first = false;
     for (int c = 0; c < batch; ++c, ++it) {
+      S.est_active = predict(it - 1);
       if (ls == 0) cy.plane_coarse(true, it == 0);   // the whole cycle in one kernel
       else cy.plane_down(0, true, it == 0);
       {
@@ -1400,7 +1416,10 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
                                                    S.d_iters, S.d_count);
         ctx.launches++;
       }
+      if (it < MGSolver::HIST_LEN)
+        SNAC_CUDA(cudaMemcpyAsync(cur + it, S.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
       if (ls > 0) {
+        S.est_active = predict(it);
         for (int l = 1; l < ls; ++l) cy.plane_down(l, false, false);
         cy.plane_coarse(false, false);
         for (int l = ls - 1; l >= 0; --l) cy.plane_up(l);
@@ -1409,7 +1428,14 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
     SNAC_CUDA(cudaMemcpyAsync(S.h_count, S.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
     SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
     if (*S.h_count == 0 || it > maxiter) break;
-    S.est_active = *S.h_count;
+    polled = *S.h_count;
+  }
+  {   // the record of this solve becomes the prediction of the next one with the same key
+    int n = 0;
+    const int ran = std::min(it, (int)MGSolver::HIST_LEN);
+    while (n < ran && cur[n] != 0) ++n;
+    S.hist_n[key] = n < ran ? n + 1 : 0;   // cycles until the counter reached zero; no record if it never did
+    S.hist_cur[key] = 1 - S.hist_cur[key];
   }
   {
     ProfScope ps(ctx, PC_MG_COARSE);
