@@ -169,10 +169,19 @@ template <class T>
 __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ CLev lv[CMAXLEV];
+  __shared__ int toff[2 * CMAXLEV + 1];   // prefix sums of the table lengths over (level, direction)
   __shared__ double red[2][32];
   T *sm = reinterpret_cast<T *>(smem_raw);
   const int q = blockIdx.x;
   if (a.active && !a.active[q]) return;
+#ifdef SNAC_COARSE_TIMING
+  __shared__ long long tstamp[48];
+  int nts = 0;
+#define TS() do { __syncthreads(); if (threadIdx.x == 0 && nts < 48) tstamp[nts] = clock64(); ++nts; } while (0)
+#else
+#define TS() do {} while (0)
+#endif
+  TS();
   const T lam = (T)(a.alpha + __ldg(a.lamq + q + 1));
   int nlev = a.nlev;
   __shared__ int s_nlev, s_nbot;
@@ -188,31 +197,40 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
       L.o1 = p; p += 5 * L.n1;
       L.o2 = p; p += 5 * L.n2;
     }
+    toff[0] = 0;
+    for (int l = 0; l < nlev; ++l) {
+      toff[2 * l + 1] = toff[2 * l] + lv[l].n1;
+      toff[2 * l + 2] = toff[2 * l + 1] + lv[l].n2;
+    }
   }
   __syncthreads();
-  // coefficient tables (global tables are 1-based with 8 doubles per entry: na_m, na_p, e, w, 1/w)
-  for (int l = 0; l < nlev; ++l) {
-    const CLev L = lv[l];
-    for (int d = 0; d < 2; ++d) {
-      const int n = d ? L.n2 : L.n1;
-      const int co = d ? L.c2 : L.c1;
-      const double *g = d ? a.lev[l].t2 : a.lev[l].t1;
-      const double *gc = l + 1 < nlev ? (d ? a.lev[l + 1].t2 : a.lev[l + 1].t1) : nullptr;
-      T *t = sm + (d ? L.o2 : L.o1);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double *e = g + 8 * (i + 1);
-        t[i] = (T)__ldg(e); t[n + i] = (T)__ldg(e + 1); t[2 * n + i] = (T)__ldg(e + 2);
-        const double w = __ldg(e + 3);
-        t[4 * n + i] = (T)w;
-        t[3 * n + i] = (gc && co) ? (T)(w / __ldg(gc + 8 * ((i >> 1) + 1) + 3)) : (T)1;
-      }
-    }
+  TS();
+  // coefficient tables (global tables are 1-based with 8 doubles per entry: na_m, na_p, e, w, 1/w): one
+  // work item per (level, direction, index), all of them in flight at once -- level after level
+  // the loop paid one global-memory latency per level and direction, 10 us of an 80 us cycle
+  for (int it = threadIdx.x; it < toff[2 * nlev]; it += blockDim.x) {
+    int k = 0;
+    while (it >= toff[k + 1]) ++k;
+    const int l = k >> 1, d = k & 1, i = it - toff[k];
+    const CLev &L = lv[l];
+    const int n = d ? L.n2 : L.n1;
+    const int co = d ? L.c2 : L.c1;
+    const double *g = d ? a.lev[l].t2 : a.lev[l].t1;
+    const double *gc = l + 1 < nlev ? (d ? a.lev[l + 1].t2 : a.lev[l + 1].t1) : nullptr;
+    T *t = sm + (d ? L.o2 : L.o1);
+    const double *e = g + 8 * (i + 1);
+    const double w = __ldg(e + 3);
+    const double wc = (gc && co) ? __ldg(gc + 8 * ((i >> 1) + 1) + 3) : w;
+    t[i] = (T)__ldg(e); t[n + i] = (T)__ldg(e + 1); t[2 * n + i] = (T)__ldg(e + 2);
+    t[4 * n + i] = (T)w;
+    t[3 * n + i] = (gc && co) ? (T)(w / wc) : (T)1;
   }
   // Depth of the hierarchy for THIS wavenumber: on a level where the shift lambda dominates the
   // diagonal, lambda >= r (e1 + e2) with r >= 1/2, Gauss-Seidel itself contracts by about
   // 1/(1+r)^2 per sweep, so that level is solved by a few sweeps and the levels below it (the
   // latency-bound tail of the cycle, run by one warp) are not visited.  Planes with a small shift
   // (the low wavenumbers, lambda -> 0) keep the whole hierarchy.
+  TS();
   if (a.adaptive && nlev > 1) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -223,7 +241,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
         const double r = e != 0.0 ? (double)lam / e : 0.0;   // > 0: the shift has the sign of the diagonal
         if (r >= 0.5) {
           nl = l + 1;
-          nb = min(a.nbot, (int)ceil(4.6 / log1p(r)));   // (1+r)^(-2 nb) <= 1e-4
+          nb = min(a.nbot, (int)ceil(2.3 / log1p(r)));   // (1+r)^(-2 nb) <= 1e-2: plenty for a coarse-grid correction
           break;
         }
       }
@@ -234,6 +252,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   } else if (threadIdx.x == 0) {
     s_nbot = a.nbot;
   }
+  TS();
   // top level: right-hand side (scaled) and iterate; rows of the plane are contiguous in memory
   {
     const CLev L = lv[0];
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
     const int lw = GB.lw(n1), W = 1 << lw, tx = threadIdx.x & (W - 1), ty = threadIdx.x >> lw, nty = blockDim.x >> lw;
     for (int i = tx; i < n1; i += W) {
       const double s1 = __ldg(a.lev[0].t1 + 8 * (i + 1) + 4);
-#pragma unroll 8
+#pragma unroll 16
       for (int j = ty; j < n2; j += nty) {
         const long o = qoff + (i + 1) + a.sy * (j + 1);
         const double s = s1 * __ldg(a.lev[0].t2 + 8 * (j + 1) + 4);
@@ -256,11 +275,13 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   // first level left to warp 0 alone (at most 256 cells); level 0 always belongs to the CTA
   int lsw = nlev;
   while (lsw > 1 && lv[lsw - 1].n1 * lv[lsw - 1].n2 <= 256) --lsw;
+  TS();
   double r2 = 0.0, b2 = 0.0;
   // ---- down leg, CTA-wide levels
   for (int l = 0; l < lsw - 1; ++l) {
     const CLev F = lv[l], C = lv[l + 1];
     c_down(sm, F, C, lam, a.npre, GB, l == 0 && a.norms, r2, b2);
+    TS();
   }
   // ---- from level lsw-1 down: restriction into the first small level by the CTA, then warp 0 runs
   //      the rest of the cycle on the small levels by itself
@@ -269,6 +290,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
       const CLev F = lv[lsw - 1], C = lv[lsw];
       c_down(sm, F, C, lam, a.npre, GB, lsw == 1 && a.norms, r2, b2);
     }
+    TS();
     if (threadIdx.x < 32) {
       for (int l = lsw; l < nlev - 1; ++l) {
         const CLev F = lv[l], C = lv[l + 1];
@@ -283,10 +305,12 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
       }
     }
     __syncthreads();
+    TS();
     {
       const CLev F = lv[lsw - 1], C = lv[lsw];
       c_up(sm, F, C, lam, a.npost, GB);
     }
+    TS();
   } else {   // the coarsest level belongs to the CTA (a single-level or all-large hierarchy)
     const CLev B = lv[nlev - 1];
     const int ns = min(nbot, B.n1 * B.n2);
@@ -305,6 +329,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   for (int l = lsw - 2; l >= 0; --l) {
     const CLev F = lv[l], C = lv[l + 1];
     c_up(sm, F, C, lam, a.npost, GB);
+    TS();
   }
   // ---- result
   {
@@ -316,6 +341,14 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
 #pragma unroll 4
       for (int j = ty; j < n2; j += nty) a.xout[qoff + (i + 1) + a.sy * (j + 1)] = (double)sm[L.ox + j * n1 + i];
   }
+  TS();
+#ifdef SNAC_COARSE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 1) {
+    printf("coarse q=1 nlev=%d lsw=%d:", nlev, lsw);
+    for (int i = 1; i < nts && i < 48; ++i) printf(" %lld", tstamp[i] - tstamp[i - 1]);
+    printf("\n");
+  }
+#endif
   if (a.norms) {
     for (int o = 16; o > 0; o >>= 1) {
       r2 += __shfl_xor_sync(0xffffffffu, r2, o);
