@@ -26,6 +26,18 @@
 
 namespace snac {
 
+// Source of a forward transform fused with fillps + updt_rhs (K3a+K3b, src/fillps.f90:29-53,
+// src/bound.f90:543-585): the right-hand side is evaluated from u,v,w inside the load stage of the
+// transform instead of being written to and read back from an array (32 instead of 48 B per point).
+struct R2RFill {
+  const double *vel[3];   // u,v,w: element (1,1,1) of arrays with the strides ist[] of the transform's input
+  const double *wq[3];    // ghosted weights (index 1..n): cell width, or 1 along the transform axis
+  const double *gq[3];    // 1, or 1/width along the transform axis
+  double cb[3][2];        // boundary right-hand-side coefficient per face (0: none)
+  double rdt;
+  int on;
+};
+
 struct R2RArgs {
   // first interior element of the input / output array; when the wavenumber axis of that side is
   // split over processes (nsplit > 1), one base per owning process, chosen by index / chunk
@@ -42,6 +54,7 @@ struct R2RArgs {
   int in_lane_t, out_lane_t;  // consecutive lanes walk along the transform axis (it has stride 1)
   double scale;
   const double *tab; // twiddles (fast) or dense matrix (generic)
+  R2RFill fill;      // forward radix kernels only
 };
 
 #define R2R_IN(t) (a.inp[a.in_split ? (t) / a.chunk : 0])
@@ -114,11 +127,15 @@ SNAC_HD void dft(Cx (&v)[R]) {
   }
 }
 
-constexpr int TP = 16;   // pencils per tile = lanes along the unit-stride direction
+#ifndef SNAC_FFT_TP
+#define SNAC_FFT_TP 32
+#endif
+constexpr int TP = SNAC_FFT_TP;   // pencils per tile = lanes along the unit-stride direction (measured 8 / 16 / 32: 2.9 / 3.3 / 3.4 TB/s)
 
 // per-thread constants of a tile
 struct Thread {
   int p, jt, tpp;      // pencil in the tile, index among the threads of that pencil, threads per pencil
+  int ip, o;           // the pencil's indices along pd and od (0-based)
   bool valid;          // the pencil exists
   long ib, ob;         // offsets of the pencil's first element in the input / output arrays
 };
@@ -130,6 +147,7 @@ SNAC_HD Thread thread_of(const R2RArgs &a, int tid, int nthr, int tile) {
   const int tpi = tile % ntp, o = tile / ntp;
   const int ip = tpi * TP + T.p;
   T.valid = ip < a.n[a.pd];
+  T.ip = ip; T.o = o;
   T.ib = ip * a.ist[a.pd] + o * a.ist[a.od];
   T.ob = ip * a.ost[a.pd] + o * a.ost[a.od];
   return T;
@@ -162,13 +180,54 @@ SNAC_HD bool is_makhoul(int kind) { return kind == K_REDFT10 || kind == K_RODFT1
 SNAC_HD bool is_sine(int kind) { return kind == K_RODFT10 || kind == K_RODFT01; }
 
 // ---- forward ---------------------------------------------------------------------------------
-template <int R1, int R2>
+// per-thread constants of the fused right-hand side (the radix kernels gather pencils along x: pd = 0)
+struct FillThread {
+  double wx, g0, w_od, g_od;
+  double bx;              // boundary terms of the faces normal to x and to od, without the weight along the axis
+  double b_od;
+  bool az;                // the transform axis is z (else y)
+};
+SNAC_HD FillThread fill_thread(const R2RArgs &a, const Thread &T) {
+  const R2RFill &f = a.fill;
+  FillThread F;
+  const int i = T.ip + 1, jo = T.o + 1;
+  F.az = a.axis == 2;
+  F.wx = SNAC_LDG(f.wq[0] + i); F.g0 = SNAC_LDG(f.gq[0] + i);
+  F.w_od = SNAC_LDG(f.wq[a.od] + jo); F.g_od = SNAC_LDG(f.gq[a.od] + jo);
+  F.bx = (i == 1 ? f.cb[0][0] : 0.0) + (i == a.n[0] ? f.cb[0][1] : 0.0);
+  F.b_od = (jo == 1 ? f.cb[a.od][0] : 0.0) + (jo == a.n[a.od] ? f.cb[a.od][1] : 0.0);
+  return F;
+}
+// right-hand side at element t of the pencil (fillps_kernel of pois.cu, same expression)
+SNAC_HD double fill_value(const R2RArgs &a, const Thread &T, const FillThread &F, int t) {
+  const R2RFill &f = a.fill;
+  const long c = T.ib + t * a.ist[a.axis];
+  const double *u = f.vel[0] + c, *vo = f.vel[a.od] + c, *va = f.vel[a.axis] + c;
+  const double du = SNAC_LDG(u) - SNAC_LDG(u - a.ist[0]);
+  const double d_od = SNAC_LDG(vo) - SNAC_LDG(vo - a.ist[a.od]);
+  const double d_ax = SNAC_LDG(va) - SNAC_LDG(va - a.ist[a.axis]);
+  const double w_ax = SNAC_LDG(f.wq[a.axis] + t + 1), g_ax = SNAC_LDG(f.gq[a.axis] + t + 1);
+  const double dv = F.az ? d_od : d_ax, dw = F.az ? d_ax : d_od;
+  const double g1 = F.az ? F.g_od : g_ax, g2 = F.az ? g_ax : F.g_od;
+  const double wx = F.wx, wy = F.az ? F.w_od : w_ax, wz = F.az ? w_ax : F.w_od;
+  double val = (dw * g2 * wx * wy + dv * g1 * wx * wz + du * F.g0 * wy * wz) * f.rdt;
+  // updt_rhs: faces normal to x, to od and to the axis
+  const double b_ax = (t == 0 ? f.cb[a.axis][0] : 0.0) + (t == a.n[a.axis] - 1 ? f.cb[a.axis][1] : 0.0);
+  val += F.bx * wy * wz;
+  val += F.az ? F.b_od * wx * wz : F.b_od * wx * wy;
+  val += F.az ? b_ax * wx * wy : b_ax * wx * wz;
+  return val;
+}
+
+template <int R1, int R2, bool FILL>
 SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
   using P = Plan<R1, R2>;
   if (!T.valid) return;
   const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
   const long isa = a.ist[a.axis];
   const double *tw = a.tab;
+  FillThread FT;
+  if (FILL) FT = fill_thread(a, T);
 #pragma unroll
   for (int j0 = 0; j0 < P::S1; j0 += P::TPP) {
     const int j = j0 + T.jt;
@@ -178,7 +237,9 @@ SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
     for (int r = 0; r < R1; ++r) {
       const int e = j + r * P::S1;
       const int t0 = tof(2 * e, P::N, makhoul), t1 = tof(2 * e + 1, P::N, makhoul);
-      double x0 = R2R_IN(t0)[T.ib + t0 * isa], x1 = R2R_IN(t1)[T.ib + t1 * isa];
+      double x0, x1;
+      if (FILL) { x0 = fill_value(a, T, FT, t0); x1 = fill_value(a, T, FT, t1); }
+      else { x0 = R2R_IN(t0)[T.ib + t0 * isa]; x1 = R2R_IN(t1)[T.ib + t1 * isa]; }
       if (sine && (t0 & 1)) x0 = -x0;
       if (sine && (t1 & 1)) x1 = -x1;
       v[r] = Cx{x0, x1};

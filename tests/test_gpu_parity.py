@@ -335,6 +335,39 @@ def test_inflow_steps_match_oracle(tmp_path, fa):
     assert divmax < 1e-9
 
 
+def test_checkpoint_restart_in_the_reference_layout(tmp_path):
+    """fld_b_###_{u,v,w,p}.bin written from the device fields (snac_b200/load.py; src/load.f90:84-187,
+    src/main.f90:1090-1117), restart from them (src/main.f90:542-556): the restarted run continues like the
+    uninterrupted one (the initial guess of the solver is lost, as in the reference: solver tolerance)."""
+    from snac_b200 import load
+    from snac_b200.sim import Simulation
+    case = cases.make("duct", str(tmp_path / "run"), fft_axis=1)
+    ini = initial_fields(case, noise=True)
+    g = Simulation(case, tol=1e-12, maxiter=200)
+    g.set_fields(ini); g.init_bc(); g.set_dt()
+    for _ in range(3):
+        g.step()
+    data = str(tmp_path / "data")
+    load.write_checkpoint(g, data)
+    load.save_geometry(data, case)
+    raw = np.fromfile(os.path.join(data, "fld_b_002_v.bin"))
+    ng = tuple(int(x) for x in case.params.blocks[1].ng)
+    assert raw.size == np.prod(ng) + 2 and raw[-1] == 3.0 and abs(raw[-2] - g.time) < 1e-15
+    r1 = [r for r, b in enumerate(case.world.boxes) if b.block == 1][0]
+    assert np.array_equal(raw[:-2].reshape(ng, order="F"), g.download(r1, L.FIELD_V)[1:-1, 1:-1, 1:-1])
+    h = Simulation(case, tol=1e-12, maxiter=200)
+    load.read_checkpoint(h, data)
+    assert h.istep == 3 and abs(h.time - g.time) < 1e-15
+    h.init_bc(); h.dt = g.dt
+    for _ in range(2):
+        g.step(); h.step()
+    for r in range(case.world.nrank):
+        a, b = g.get_fields(r), h.get_fields(r)
+        for k in "uvw":
+            assert rel(b[k], a[k]) < 1e-9, (k, r)
+    g.close(); h.close()
+
+
 @pytest.mark.parametrize("fft_axis", [0, 1])
 def test_ldc_golden_vector_on_gpu(fft_axis):
     """The reference's own test (tests/lid_driven_cavity/test.py:5-16) run through the CUDA path:

@@ -1,0 +1,55 @@
+"""Field/checkpoint files in the reference's layout (snac_b200/load.py; reference src/load.f90:84-187,
+src/initgrid.f90:128-165, src/main.f90:428-438): written box by box, read back the way the reference's own
+readers do (utils/read_binary_data/python/read_single_field_binary.py: np.fromfile + Fortran-order reshape)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from snac_b200 import load
+from snac_b200.initgrid import load_grid
+
+
+def test_load_one_writes_the_reference_layout(tmp_path):
+    ng = (6, 5, 4)
+    rng = np.random.default_rng(3)
+    full = rng.standard_normal(ng)
+    fn = str(tmp_path / "fld_b_001_u.bin")
+    # two boxes of one block split in y, one ghost layer each (nh = 1), written independently
+    for lo, hi, first in (((1, 1, 1), (6, 2, 4), True), ((1, 3, 1), (6, 5, 4), False)):
+        n = [hi[d] - lo[d] + 1 for d in range(3)]
+        p = np.full([x + 2 for x in n], np.nan, order="F")
+        p[1:-1, 1:-1, 1:-1] = full[lo[0] - 1:hi[0], lo[1] - 1:hi[1], lo[2] - 1:hi[2]]
+        load.load_one("w", fn, ng, lo, hi, p, time=1.25, istep=42, write_info=first)
+    assert os.path.getsize(fn) == (np.prod(ng) + 2) * 8          # src/load.f90:110
+    raw = np.fromfile(fn, dtype="float64")                        # the reference reader's way
+    assert np.array_equal(raw[:-2].reshape(ng, order="F"), full)
+    assert raw[-2] == 1.25 and raw[-1] == 42.0
+    # read a box back
+    p = np.zeros((8, 5, 6), order="F")
+    t, it = load.load_one("r", fn, ng, (1, 3, 1), (6, 5, 4), p)
+    assert (t, it) == (1.25, 42)
+    assert np.array_equal(p[1:-1, 1:-1, 1:-1], full[:, 2:5, :])
+    assert np.all(p[0] == 0.0)                                    # ghost cells are not touched
+    # a file of the wrong size is refused, as in the reference (src/load.f90:112-119)
+    with open(fn, "ab") as f:
+        f.write(b"\0" * 8)
+    with pytest.raises(IOError):
+        load.load_one("r", fn, ng, (1, 1, 1), (6, 2, 4), np.zeros((8, 4, 6), order="F"))
+
+
+def test_geometry_and_grid_files_round_trip(tmp_path):
+    case = cases.make("channel", str(tmp_path / "run"), fft_axis=2)
+    out = str(tmp_path / "data")
+    load.save_geometry(out, case)
+    geo = np.loadtxt(os.path.join(out, "geometry_b_001.out"), max_rows=4)   # as read_single_field_binary.py does
+    blk = case.params.blocks[0]
+    assert np.array_equal((geo[1] - geo[0] + 1).astype(int), np.asarray(blk.ng))
+    assert np.allclose(geo[2], blk.lmin) and np.allclose(geo[3], blk.lmax)
+    for d, c in enumerate("xyz"):
+        g = load_grid(os.path.join(out, f"grid_{c}_b_001"), int(blk.ng[d]))
+        ref = case.bgrids[0][d]
+        assert np.array_equal(g.rf[1:-1], ref.rf[1:-1]) and np.array_equal(g.drc[1:-1], ref.drc[1:-1])
+        raw = np.fromfile(os.path.join(out, f"grid_{c}_b_001.bin")).reshape((int(blk.ng[d]), 4), order="F")
+        assert np.array_equal(raw[:, 1], ref.rc[1:-1])            # column 1 = cell centres (reference reader)
