@@ -144,7 +144,23 @@ static std::vector<BlockInfo> assemble_blocks(Ctx &ctx) {
   return blocks;
 }
 
+// Which wavenumbers does process `proc` solve?  Cyclic (q mod nproc == proc) when the number of
+// processes is a power of two: the cycles a plane needs fall with its wavenumber, so consecutive
+// chunks would leave the process holding the lowest ones working while the others wait.
+// Returns the first wavenumber q0 and the count (as q1 - q0); wavenumber k of the slab is
+// q0 + k * q_stride(ctx).
+static bool q_is_cyclic(const Ctx &ctx) {
+  static const bool off = getenv("SNAC_SLAB_CYCLIC") && atoi(getenv("SNAC_SLAB_CYCLIC")) == 0;
+  const int np = ctx.comm.nproc;
+  return !off && np > 1 && (np & (np - 1)) == 0;
+}
+static int q_stride(const Ctx &ctx) { return q_is_cyclic(ctx) ? ctx.comm.nproc : 1; }
 static void q_range(const Ctx &ctx, int nq, int proc, int &q0, int &q1) {
+  if (q_is_cyclic(ctx)) {
+    q0 = std::min(nq, proc);
+    q1 = q0 + (nq > proc ? (nq - proc + ctx.comm.nproc - 1) / ctx.comm.nproc : 0);
+    return;
+  }
   const int chunk = (nq + ctx.comm.nproc - 1) / ctx.comm.nproc;
   q0 = std::min(nq, proc * chunk);
   q1 = std::min(nq, q0 + chunk);
@@ -344,7 +360,7 @@ static void commit(Ctx &ctx) {
         std::vector<double> l = r2r_eigenvalues(ctx.nq, bc, true);
         const double dl = w0.dl[fa][0];
         s.lam.assign((size_t)(ctx.q1 - ctx.q0) + 2, 0.0);
-        for (int k = ctx.q0; k < ctx.q1; ++k) s.lam[k - ctx.q0 + 1] = l[k] / (dl * dl);
+        for (int k = 0; k < ctx.q1 - ctx.q0; ++k) s.lam[k + 1] = l[ctx.q0 + k * q_stride(ctx)] / (dl * dl);
         if (ctx.comm.nproc > 1) {   // slabs live in the arena: peers write the right-hand side and read the solution
           Grid3 sg = Grid3::make(s.n[0], s.n[1], std::max(s.n[2], 1));
           s.x = ctx.comm.alloc(sg.alloc_elems(), B.id, AK_SLAB_X) + 15;
@@ -444,15 +460,18 @@ static void finish_setup(Ctx &ctx) {
       for (int sd = 0; sd < 2; ++sd) off += (long)(b.info.lo[S.perm[sd]] - ctx.blocks_lo[bi][S.perm[sd]]) * sg.st(sd);
       R.chunk = (ctx.nq + ctx.comm.nproc - 1) / ctx.comm.nproc;
       R.nsplit = ctx.comm.nproc;
+      R.cyclic = q_is_cyclic(ctx);
       for (int p = 0; p < ctx.comm.nproc; ++p) {
         int q0, q1;
         q_range(ctx, ctx.nq, p, q0, q1);
         double *xb, *bb;
         if (p == ctx.comm.me) { xb = S.xcur(bi); bb = S.bcur(bi); }
         else { xb = ctx.comm.remote(p, b.info.block, AK_SLAB_X) + 15; bb = ctx.comm.remote(p, b.info.block, AK_SLAB_B) + 15; }
-        // the wavenumber index is absolute in the kernels: shift by the slab origin
-        R.x[p] = xb + off - (long)q0 * sg.st(2);
-        R.b[p] = bb + off - (long)q0 * sg.st(2);
+        // chunks: the wavenumber index is absolute in the kernels, shift by the slab origin; cyclic: the
+        // kernels divide the index by the number of processes themselves
+        const long shift = q_is_cyclic(ctx) ? 0 : (long)q0 * sg.st(2);
+        R.x[p] = xb + off - shift;
+        R.b[p] = bb + off - shift;
       }
     }
     (void)fa;
@@ -642,13 +661,13 @@ static void do_fft(Ctx &ctx, int dir, double dtrk = 0.0) {
         }
         f.rdt = 1.0 / dtrk;
         f.on = 1;
-        r2r_execute(ctx, ctx.plan_p, +1, b.g.n, in, 1, pst, R.b, R.nsplit, R.st, R.chunk, 1.0, &f);
+        r2r_execute(ctx, ctx.plan_p, +1, b.g.n, in, 1, pst, R.b, R.nsplit, R.st, R.chunk, 1.0, &f, R.cyclic);
       } else {
-        r2r_execute(ctx, ctx.plan_p, +1, b.g.n, in, 1, pst, R.b, R.nsplit, R.st, R.chunk, 1.0);
+        r2r_execute(ctx, ctx.plan_p, +1, b.g.n, in, 1, pst, R.b, R.nsplit, R.st, R.chunk, 1.0, nullptr, R.cyclic);
       }
     } else {              // the owners' solution slabs -> physical pp, times normfft (src/main.f90:1017-1020)
       double *out[1] = {b.pp.p + pint};
-      r2r_execute(ctx, ctx.plan_p, -1, b.g.n, R.x, R.nsplit, R.st, out, 1, pst, R.chunk, ctx.plan_p.normfft);
+      r2r_execute(ctx, ctx.plan_p, -1, b.g.n, R.x, R.nsplit, R.st, out, 1, pst, R.chunk, ctx.plan_p.normfft, nullptr, R.cyclic);
     }
   }
   // forward: every process must have received all pieces of its slabs before solving

@@ -156,6 +156,7 @@ struct FFTRoute {
   long st[3] = {0, 0, 0};          // strides of the physical directions in the solver arrays
   double *x[16] = {nullptr}, *b[16] = {nullptr};
   int chunk = 1, nsplit = 1;
+  bool cyclic = false;             // wavenumber q is solved by process q mod nproc (else: consecutive chunks)
 };
 
 // One ghosted array per local box taking part in an exchange.
@@ -226,12 +227,13 @@ std::vector<double> r2r_eigenvalues(int n, const char bc[2], bool centered);
 // in/out address the first interior element; ist/ost are the strides of the physical directions
 // x,y,z in each array (in == out with equal strides is allowed); out *= scale
 // in_split/out_split > 1: that side's transform axis is split into chunks of `chunk` indices, one
-// base pointer per chunk (the owning process' slab, possibly in a peer's memory)
+// base pointer per chunk (the owning process' slab, possibly in a peer's memory); cyclic: index t of the axis
+// lives in piece t mod nsplit at position t div nsplit instead
 struct R2RFill;   // fft_radix.cuh: forward transform fused with fillps + updt_rhs
 bool r2r_can_fill(const R2RPlan &pl, const int n3[3], const long ist[3], const long ost[3]);
 void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *const *in, int in_split,
                  const long ist[3], double *const *out, int out_split, const long ost[3], int chunk, double scale,
-                 const R2RFill *fill = nullptr);
+                 const R2RFill *fill = nullptr, bool cyclic = false);
 
 // ------------------------------------------------------------------------------------------
 // multigrid (mg.cu)
@@ -451,7 +453,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   bool committed = false;
   bool ready = false;                       // exchanges and routing built (after snac_comm_connect when nproc > 1)
-  int nq = 1, q0 = 0, q1 = 1;               // wavenumbers of the run and the slab solved by this process
+  int nq = 1, q0 = 0, q1 = 1;               // wavenumbers of the run and the slab solved by this process (q1 - q0 of them)
+  bool q_cyclic = false;                    // ... which are q0 + k nproc (cyclic) instead of q0 + k
   std::vector<int> block_index;             // block id -> solver box
   std::vector<std::array<int, 3>> blocks_lo;
   std::vector<FFTRoute> route;              // per local box

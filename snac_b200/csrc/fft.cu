@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) r2r_dense_kernel(const R2RArgs a) {
   const int nfull = a.n[a.axis];
   FOR_ITEMS(a.in_lane_t, nfull, {
     long ib, ob;
-    if (pencil_base(a, blockIdx.x, p, ib, ob)) T[t * tpp + p] = R2R_IN(t)[ib + t * isa];
+    if (pencil_base(a, blockIdx.x, p, ib, ob)) T[t * tpp + p] = R2R_IN_AT(t, ib, isa);
   })
   __syncthreads();
   FOR_ITEMS(a.out_lane_t, nfull, {
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) r2r_dense_kernel(const R2RArgs a) {
       } else {
         acc = T[t * tpp + p];  // entries beyond the transform length (staggered, q = 1) pass through
       }
-      R2R_OUT(t)[ob + t * osa] = acc * a.scale;
+      R2R_OUT_AT(t, ob, osa) = acc * a.scale;
     }
   })
 }
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
     FOR_ITEMS(a.in_lane_t, n, {
       long ib, ob;
       if (pencil_base(a, blockIdx.x, p, ib, ob)) {
-        double v = R2R_IN(t)[ib + t * isa];
+        double v = R2R_IN_AT(t, ib, isa);
         int slot = t;
         if (makhoul) {
           if (sine && (t & 1)) v = -v;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
         const C2 xmk{e.x - wo.x, -(e.y - wo.y)};    // X[m-k]
         const int ka = k, kb = m - k;               // the two output wavenumbers (k=0: 0 and m)
         const double sc = a.scale;
-#define OUT_AT(idx) R2R_OUT(idx)[ob + (idx) * osa]
+#define OUT_AT(idx) R2R_OUT_AT(idx, ob, osa)
         if (!makhoul) {
           OUT_AT(ka) = sc * xk.x;
           if (k > 0) OUT_AT(n - ka) = sc * xk.y;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
       long ib, ob;
       const int k = t;
       if (pencil_base(a, blockIdx.x, p, ib, ob)) {
-#define IN_AT(idx) R2R_IN(idx)[ib + (idx) * isa]
+#define IN_AT(idx) R2R_IN_AT(idx, ib, isa)
         const int kb = m - k;
         C2 xk, xm;  // X[k], X[m-k]
         if (!makhoul) {
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
         if (makhoul) slot = (t & 1) ? (n - 1 - (t >> 1)) : (t >> 1);
         double v = T[slot * tpp + p] * a.scale;
         if (makhoul && sine && (t & 1)) v = -v;
-        R2R_OUT(t)[ob + t * osa] = v;
+        R2R_OUT_AT(t, ob, osa) = v;
       }
     })
   }
@@ -429,7 +429,7 @@ bool r2r_can_fill(const R2RPlan &pl, const int n3[3], const long ist[3], const l
 
 void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *const *in, int in_split,
                  const long ist[3], double *const *out, int out_split, const long ost[3], int chunk, double scale,
-                 const R2RFill *fill) {
+                 const R2RFill *fill, bool cyclic) {
   R2RArgs a;
   a.fill.on = 0;
   if (fill) {
@@ -440,7 +440,15 @@ void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const do
   for (int p = 0; p < 16; ++p) { a.inp[p] = nullptr; a.outp[p] = nullptr; }
   for (int p = 0; p < std::max(in_split, 1); ++p) a.inp[p] = in[p];
   for (int p = 0; p < std::max(out_split, 1); ++p) a.outp[p] = out[p];
-  a.in_split = in_split > 1; a.out_split = out_split > 1; a.chunk = std::max(chunk, 1);
+  const int mode = cyclic ? 2 : 1;
+  a.in_split = in_split > 1 ? mode : 0; a.out_split = out_split > 1 ? mode : 0; a.chunk = std::max(chunk, 1);
+  a.ns_mask = 0; a.ns_shift = 0;
+  if (cyclic) {
+    const int ns = std::max(in_split, out_split);
+    if (ns < 1 || (ns & (ns - 1))) throw Error("r2r_execute: a cyclic split needs a power-of-two number of pieces");
+    a.ns_mask = ns - 1;
+    while ((1 << a.ns_shift) < ns) ++a.ns_shift;
+  }
   for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = ist[d]; a.ost[d] = ost[d]; }
   a.axis = pl.axis;
   a.nt = pl.nt;

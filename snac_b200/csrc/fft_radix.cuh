@@ -43,7 +43,8 @@ struct R2RArgs {
   // split over processes (nsplit > 1), one base per owning process, chosen by index / chunk
   const double *inp[16];
   double *outp[16];
-  int in_split, out_split, chunk;
+  int in_split, out_split, chunk;   // see R2R_WHO / R2R_POS
+  int ns_mask, ns_shift;
   long ist[3], ost[3];  // strides of the physical directions x,y,z in the input / output arrays
   int n[3];
   int axis;
@@ -57,8 +58,15 @@ struct R2RArgs {
   R2RFill fill;      // forward radix kernels only
 };
 
-#define R2R_IN(t) (a.inp[a.in_split ? (t) / a.chunk : 0])
-#define R2R_OUT(t) (a.outp[a.out_split ? (t) / a.chunk : 0])
+// element t of a pencil whose first element is at offset `base` and whose axis stride is `st`.
+// split = 0: one array.  split = 1: the axis is cut into consecutive chunks of `chunk` indices, one
+// array per chunk (bases shifted by the chunk origin).  split = 2: cyclic, index t lives in array
+// t mod ns at position t div ns (ns a power of two): every process owns low and high wavenumbers
+// alike, which balances the solver's work per process (low wavenumbers need the most cycles).
+#define R2R_WHO(split, t) ((split) == 0 ? 0 : ((split) == 1 ? (t) / a.chunk : ((t) & a.ns_mask)))
+#define R2R_POS(split, t) ((split) == 2 ? ((t) >> a.ns_shift) : (t))
+#define R2R_IN_AT(t, base, st) a.inp[R2R_WHO(a.in_split, t)][(base) + (long)R2R_POS(a.in_split, t) * (st)]
+#define R2R_OUT_AT(t, base, st) a.outp[R2R_WHO(a.out_split, t)][(base) + (long)R2R_POS(a.out_split, t) * (st)]
 
 #if defined(__CUDA_ARCH__)
 #define SNAC_LDG(p) __ldg(p)
@@ -239,7 +247,7 @@ SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
       const int t0 = tof(2 * e, P::N, makhoul), t1 = tof(2 * e + 1, P::N, makhoul);
       double x0, x1;
       if (FILL) { x0 = fill_value(a, T, FT, t0); x1 = fill_value(a, T, FT, t1); }
-      else { x0 = R2R_IN(t0)[T.ib + t0 * isa]; x1 = R2R_IN(t1)[T.ib + t1 * isa]; }
+      else { x0 = R2R_IN_AT(t0, T.ib, isa); x1 = R2R_IN_AT(t1, T.ib, isa); }
       if (sine && (t0 & 1)) x0 = -x0;
       if (sine && (t1 & 1)) x1 = -x1;
       v[r] = Cx{x0, x1};
@@ -305,7 +313,7 @@ SNAC_HD void fwd_untangle(const R2RArgs &a, const double2 *Z, const Thread &T) {
     const Cx xk{e.x + wo.x, e.y + wo.y};        // X[k]
     const Cx xmk{e.x - wo.x, -(e.y - wo.y)};    // X[m-k]
     const int ka = k, kb = m - k;               // the two output wavenumbers (k=0: 0 and m)
-#define SNAC_OUT_AT(idx) R2R_OUT(idx)[ob + (idx) * osa]
+#define SNAC_OUT_AT(idx) R2R_OUT_AT(idx, ob, osa)
     if (!makhoul) {
       SNAC_OUT_AT(ka) = sc * xk.x;
       if (k > 0) SNAC_OUT_AT(n - ka) = sc * xk.y;
@@ -346,7 +354,7 @@ SNAC_HD void bwd_tangle(const R2RArgs &a, double2 *Z, const Thread &T) {
   for (int k0 = 0; k0 < nk; k0 += P::TPP) {
     const int k = k0 + T.jt;
     if (k >= nk) break;
-#define SNAC_IN_AT(idx) R2R_IN(idx)[ib + (idx) * isa]
+#define SNAC_IN_AT(idx) R2R_IN_AT(idx, ib, isa)
     const int kb = m - k;
     Cx xk, xm;  // X[k], X[m-k]
     if (!makhoul) {
@@ -399,8 +407,8 @@ SNAC_HD void bwd_pass2(const R2RArgs &a, const double2 *Z, const Thread &T) {   
       double x0 = v[r].x * a.scale, x1 = v[r].y * a.scale;
       if (sine && (t0 & 1)) x0 = -x0;
       if (sine && (t1 & 1)) x1 = -x1;
-      R2R_OUT(t0)[T.ob + t0 * osa] = x0;
-      R2R_OUT(t1)[T.ob + t1 * osa] = x1;
+      R2R_OUT_AT(t0, T.ob, osa) = x0;
+      R2R_OUT_AT(t1, T.ob, osa) = x1;
     }
   }
 }

@@ -53,7 +53,7 @@ int main() {
   for (int n : {32, 64, 128, 256, 512})
     for (int axis : {1, 2})
       for (int kind : kinds)
-        for (int split : {1, 2}) {
+        for (int split : {1, 2, -2, -4}) {   // one array; two consecutive chunks; cyclic over two / four arrays
           // box: 21 pencils along x (a partial second tile), 3 along the other direction
           int n3[3] = {21, 3, 3};
           n3[axis] = n;
@@ -65,24 +65,32 @@ int main() {
           long sst[3];
           sst[pd] = 1; sst[od] = 24; sst[axis] = 24L * n3[od];
           const size_t pe = (size_t)psz * (n3[2] + 2) + 64, se = (size_t)sst[axis] * n + 64;
-          std::vector<double> phys(pe, 0.0), spec(se, 0.0), spec2(se, 0.0);
+          std::vector<double> phys(pe, 0.0), spec(se, 0.0), spec2(se, 0.0), spec3(se, 0.0), spec4(se, 0.0);
+          std::vector<double> *pieces[4] = {&spec, &spec2, &spec3, &spec4};
+          const int ncyc = split < 0 ? -split : 0;
           const long pint = 1 + psy + psz;
           const std::vector<double> tab = r2r_fast_tables(n);
           const std::vector<double> Mx = dense_matrix(kind, n);
           R2RArgs a;
           for (int p = 0; p < 16; ++p) { a.inp[p] = nullptr; a.outp[p] = nullptr; }
-          const int chunk = split > 1 ? n / 2 : n;
+          const int chunk = split == 2 ? n / 2 : n;
           // the split side is the spectral one: two "owners", each holding half of the wavenumbers
           // in its own array (here: the same layout, second half in spec2)
           for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = fwd ? pst[d] : sst[d]; a.ost[d] = fwd ? sst[d] : pst[d]; }
           a.axis = axis; a.nt = n; a.tp = radix::TP; a.pd = pd; a.od = od; a.kind = kind;
           a.in_lane_t = a.out_lane_t = 0; a.scale = 0.75; a.tab = tab.data(); a.chunk = chunk; a.fill.on = 0;
+          a.ns_mask = ncyc ? ncyc - 1 : 0; a.ns_shift = ncyc == 4 ? 2 : (ncyc == 2 ? 1 : 0);
           std::vector<double> in((size_t)n3[0] * n3[1] * n3[2]);
           for (auto &v : in) v = U(rng);
           auto lin = [&](int i, int j, int k) { return ((size_t)k * n3[1] + j) * n3[0] + i; };
           auto spec_at = [&](int i, int j, int k) -> double & {
             const int idx[3] = {i, j, k};
             const int t = idx[axis];
+            if (ncyc) {   // index t lives in piece t mod ncyc at position t div ncyc
+              int id2[3] = {i, j, k};
+              id2[axis] = t / ncyc;
+              return (*pieces[t % ncyc])[id2[0] * sst[0] + id2[1] * sst[1] + id2[2] * sst[2]];
+            }
             std::vector<double> &arr = (split > 1 && t >= chunk) ? spec2 : spec;
             return arr[idx[0] * sst[0] + idx[1] * sst[1] + idx[2] * sst[2]];
           };
@@ -90,11 +98,13 @@ int main() {
             for (int k = 0; k < n3[2]; ++k) for (int j = 0; j < n3[1]; ++j) for (int i = 0; i < n3[0]; ++i)
               phys[pint + i + psy * j + psz * k] = in[lin(i, j, k)];
             a.inp[0] = phys.data() + pint; a.in_split = 0;
-            a.outp[0] = spec.data(); a.outp[1] = spec2.data(); a.out_split = split > 1;
+            a.outp[0] = spec.data(); a.outp[1] = spec2.data(); a.outp[2] = spec3.data(); a.outp[3] = spec4.data();
+            a.out_split = ncyc ? 2 : (split > 1 ? 1 : 0);
           } else {
             for (int k = 0; k < n3[2]; ++k) for (int j = 0; j < n3[1]; ++j) for (int i = 0; i < n3[0]; ++i)
               spec_at(i, j, k) = in[lin(i, j, k)];
-            a.inp[0] = spec.data(); a.inp[1] = spec2.data(); a.in_split = split > 1;
+            a.inp[0] = spec.data(); a.inp[1] = spec2.data(); a.inp[2] = spec3.data(); a.inp[3] = spec4.data();
+            a.in_split = ncyc ? 2 : (split > 1 ? 1 : 0);
             a.outp[0] = phys.data() + pint; a.out_split = 0;
           }
           const long ntiles = (long)((n3[pd] + radix::TP - 1) / radix::TP) * n3[od];
@@ -155,7 +165,7 @@ int main() {
         for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = pst[d]; a.ost[d] = sst[d]; }
         a.axis = axis; a.nt = n; a.tp = radix::TP; a.pd = pd; a.od = od; a.kind = kind;
         a.in_lane_t = a.out_lane_t = 0; a.scale = 1.0; a.tab = tab.data(); a.chunk = n;
-        a.in_split = a.out_split = 0; a.outp[0] = spec.data();
+        a.in_split = a.out_split = 0; a.ns_mask = a.ns_shift = 0; a.outp[0] = spec.data();
         a.fill.on = 1; a.fill.rdt = rdt;
         a.fill.vel[0] = u.data() + pint; a.fill.vel[1] = v.data() + pint; a.fill.vel[2] = w.data() + pint;
         for (int d = 0; d < 3; ++d) { a.fill.wq[d] = wq[d].data(); a.fill.gq[d] = gq[d].data(); a.fill.cb[d][0] = cb[d][0]; a.fill.cb[d][1] = cb[d][1]; }
