@@ -459,6 +459,7 @@ static void finish_setup(Ctx &ctx) {
       long off = 1 + sg.sy + sg.sz;
       for (int sd = 0; sd < 2; ++sd) off += (long)(b.info.lo[S.perm[sd]] - ctx.blocks_lo[bi][S.perm[sd]]) * sg.st(sd);
       R.chunk = (ctx.nq + ctx.comm.nproc - 1) / ctx.comm.nproc;
+      R.off = off;
       R.nsplit = ctx.comm.nproc;
       R.cyclic = q_is_cyclic(ctx);
       for (int p = 0; p < ctx.comm.nproc; ++p) {
@@ -675,6 +676,13 @@ static void do_fft(Ctx &ctx, int dir, double dtrk = 0.0) {
 }
 static void do_solve(Ctx &ctx) {
   ctx.psolver.solve(ctx);
+  if (ctx.psolver.swapped) {   // one process: the solution array traded places with the solver's second buffer
+    for (int lb = 0; lb < (int)ctx.boxes.size(); ++lb) {
+      FFTRoute &R = ctx.route[lb];
+      R.x[0] = ctx.psolver.xcur(ctx.block_index[ctx.boxes[lb]->info.block]) + R.off;
+    }
+    ctx.psolver.swapped = false;
+  }
   // batched: the peers read this process' solution slab in the backward transform
   if (ctx.prm.fft_axis > 0) ctx.comm.handshake(ctx, CH_SOLVED, ~0u);
 }

@@ -156,6 +156,7 @@ struct FFTRoute {
   long st[3] = {0, 0, 0};          // strides of the physical directions in the solver arrays
   double *x[16] = {nullptr}, *b[16] = {nullptr};
   int chunk = 1, nsplit = 1;
+  long off = 0;                    // first cell of the box inside its block's solver array
   bool cyclic = false;             // wavenumber q is solved by process q mod nproc (else: consecutive chunks)
 };
 
@@ -358,6 +359,7 @@ struct MGSolver {
   void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched, int max_levels = 24);
   void solve(Ctx &ctx);
   const Grid3 &grid0(int lb) const { return levels[0]->boxes[lb].g; }
+  bool swapped = false;            // the level-0 iterate moved to the other buffer during the last solve (plane-local path)
   double *xcur(int lb) const { return levels[0]->boxes[lb].xp; }
   double *bcur(int lb) const { return levels[0]->boxes[lb].bp; }
 };

@@ -368,38 +368,46 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
 }
 
 // register-radix kernels (fft_radix.cuh): one CTA per tile of 32 pencils
-template <int R1, int R2, bool FWD, bool FILL = false>
+template <int R1, int R2, bool FWD, bool FILL, bool SPLIT>
 __global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS) r2r_radix_kernel(const R2RArgs a) {
   extern __shared__ __align__(16) double2 Zs[];
   const radix::Thread T = radix::thread_of(a, threadIdx.x, blockDim.x, blockIdx.x);
   if (FWD) {
-    radix::fwd_pass1<R1, R2, FILL>(a, Zs, T);
+    radix::fwd_pass1<R1, R2, FILL, SPLIT>(a, Zs, T);
     __syncthreads();
     radix::run_pass<R1, R2, false>(a, Zs, T);
     __syncthreads();
-    radix::fwd_untangle<R1, R2>(a, Zs, T);
+    radix::fwd_untangle<R1, R2, SPLIT>(a, Zs, T);
   } else {
-    radix::bwd_tangle<R1, R2>(a, Zs, T);
+    radix::bwd_tangle<R1, R2, SPLIT>(a, Zs, T);
     __syncthreads();
     radix::run_pass<R1, R2, true>(a, Zs, T);
     __syncthreads();
-    radix::bwd_pass2<R1, R2>(a, Zs, T);
+    radix::bwd_pass2<R1, R2, SPLIT>(a, Zs, T);
   }
+}
+
+template <int R1, int R2, bool FWD, bool FILL, bool SPLIT>
+static void radix_go1(cudaStream_t st, const R2RArgs &a, long ntiles) {
+  using P = radix::Plan<R1, R2>;
+  static bool attr = false;
+  if (!attr && P::SMEM > 48 * 1024) {
+    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, FWD, FILL, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+    attr = true;
+  }
+  r2r_radix_kernel<R1, R2, FWD, FILL, SPLIT><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
 }
 
 template <int R1, int R2>
 static void radix_go(cudaStream_t st, const R2RArgs &a, int dir, long ntiles) {
-  using P = radix::Plan<R1, R2>;
-  static bool attr = false;
-  if (!attr && P::SMEM > 48 * 1024) {
-    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
-    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
-    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
-    attr = true;
+  const bool split = a.in_split != 0 || a.out_split != 0;
+  if (dir > 0 && a.fill.on) {
+    if (split) radix_go1<R1, R2, true, true, true>(st, a, ntiles); else radix_go1<R1, R2, true, true, false>(st, a, ntiles);
+  } else if (dir > 0) {
+    if (split) radix_go1<R1, R2, true, false, true>(st, a, ntiles); else radix_go1<R1, R2, true, false, false>(st, a, ntiles);
+  } else {
+    if (split) radix_go1<R1, R2, false, false, true>(st, a, ntiles); else radix_go1<R1, R2, false, false, false>(st, a, ntiles);
   }
-  if (dir > 0 && a.fill.on) r2r_radix_kernel<R1, R2, true, true><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
-  else if (dir > 0) r2r_radix_kernel<R1, R2, true><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
-  else r2r_radix_kernel<R1, R2, false><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
 }
 
 // transform lengths served by the radix kernels: n = 2 R1 R2

@@ -67,6 +67,10 @@ struct R2RArgs {
 #define R2R_POS(split, t) ((split) == 2 ? ((t) >> a.ns_shift) : (t))
 #define R2R_IN_AT(t, base, st) a.inp[R2R_WHO(a.in_split, t)][(base) + (long)R2R_POS(a.in_split, t) * (st)]
 #define R2R_OUT_AT(t, base, st) a.outp[R2R_WHO(a.out_split, t)][(base) + (long)R2R_POS(a.out_split, t) * (st)]
+// the radix kernels are compiled twice: SPLIT = false (one process: one array on either side) keeps the
+// address arithmetic of the unrolled butterflies free of the selects above
+#define R2R_IN_ATS(t, base, st) (SPLIT ? R2R_IN_AT(t, base, st) : a.inp[0][(base) + (t) * (st)])
+#define R2R_OUT_ATS(t, base, st) (SPLIT ? R2R_OUT_AT(t, base, st) : a.outp[0][(base) + (t) * (st)])
 
 #if defined(__CUDA_ARCH__)
 #define SNAC_LDG(p) __ldg(p)
@@ -227,7 +231,7 @@ SNAC_HD double fill_value(const R2RArgs &a, const Thread &T, const FillThread &F
   return val;
 }
 
-template <int R1, int R2, bool FILL>
+template <int R1, int R2, bool FILL, bool SPLIT>
 SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
   using P = Plan<R1, R2>;
   if (!T.valid) return;
@@ -247,7 +251,7 @@ SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
       const int t0 = tof(2 * e, P::N, makhoul), t1 = tof(2 * e + 1, P::N, makhoul);
       double x0, x1;
       if (FILL) { x0 = fill_value(a, T, FT, t0); x1 = fill_value(a, T, FT, t1); }
-      else { x0 = R2R_IN_AT(t0, T.ib, isa); x1 = R2R_IN_AT(t1, T.ib, isa); }
+      else { x0 = R2R_IN_ATS(t0, T.ib, isa); x1 = R2R_IN_ATS(t1, T.ib, isa); }
       if (sine && (t0 & 1)) x0 = -x0;
       if (sine && (t1 & 1)) x1 = -x1;
       v[r] = Cx{x0, x1};
@@ -290,7 +294,7 @@ SNAC_HD void run_pass(const R2RArgs &a, double2 *Z, const Thread &T) {   // radi
   }
 }
 
-template <int R1, int R2>
+template <int R1, int R2, bool SPLIT>
 SNAC_HD void fwd_untangle(const R2RArgs &a, const double2 *Z, const Thread &T) {
   using P = Plan<R1, R2>;
   if (!T.valid) return;
@@ -313,7 +317,7 @@ SNAC_HD void fwd_untangle(const R2RArgs &a, const double2 *Z, const Thread &T) {
     const Cx xk{e.x + wo.x, e.y + wo.y};        // X[k]
     const Cx xmk{e.x - wo.x, -(e.y - wo.y)};    // X[m-k]
     const int ka = k, kb = m - k;               // the two output wavenumbers (k=0: 0 and m)
-#define SNAC_OUT_AT(idx) R2R_OUT_AT(idx, ob, osa)
+#define SNAC_OUT_AT(idx) R2R_OUT_ATS(idx, ob, osa)
     if (!makhoul) {
       SNAC_OUT_AT(ka) = sc * xk.x;
       if (k > 0) SNAC_OUT_AT(n - ka) = sc * xk.y;
@@ -341,7 +345,7 @@ SNAC_HD void fwd_untangle(const R2RArgs &a, const double2 *Z, const Thread &T) {
 }
 
 // ---- backward --------------------------------------------------------------------------------
-template <int R1, int R2>
+template <int R1, int R2, bool SPLIT>
 SNAC_HD void bwd_tangle(const R2RArgs &a, double2 *Z, const Thread &T) {
   using P = Plan<R1, R2>;
   if (!T.valid) return;
@@ -354,7 +358,7 @@ SNAC_HD void bwd_tangle(const R2RArgs &a, double2 *Z, const Thread &T) {
   for (int k0 = 0; k0 < nk; k0 += P::TPP) {
     const int k = k0 + T.jt;
     if (k >= nk) break;
-#define SNAC_IN_AT(idx) R2R_IN_AT(idx, ib, isa)
+#define SNAC_IN_AT(idx) R2R_IN_ATS(idx, ib, isa)
     const int kb = m - k;
     Cx xk, xm;  // X[k], X[m-k]
     if (!makhoul) {
@@ -383,7 +387,7 @@ SNAC_HD void bwd_tangle(const R2RArgs &a, double2 *Z, const Thread &T) {
   }
 }
 
-template <int R1, int R2>
+template <int R1, int R2, bool SPLIT>
 SNAC_HD void bwd_pass2(const R2RArgs &a, const double2 *Z, const Thread &T) {   // radix R1 at stride S1, then the store
   using P = Plan<R1, R2>;
   if (!T.valid) return;
@@ -407,8 +411,8 @@ SNAC_HD void bwd_pass2(const R2RArgs &a, const double2 *Z, const Thread &T) {   
       double x0 = v[r].x * a.scale, x1 = v[r].y * a.scale;
       if (sine && (t0 & 1)) x0 = -x0;
       if (sine && (t1 & 1)) x1 = -x1;
-      R2R_OUT_AT(t0, T.ob, osa) = x0;
-      R2R_OUT_AT(t1, T.ob, osa) = x1;
+      R2R_OUT_ATS(t0, T.ob, osa) = x0;
+      R2R_OUT_ATS(t1, T.ob, osa) = x1;
     }
   }
 }

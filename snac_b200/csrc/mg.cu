@@ -831,9 +831,10 @@ __global__ void mg_flags_kernel(double *norms, int nq, double tol2, int it, int 
   if (threadIdx.x == 0) *count = cnt;
 }
 
-__global__ void mg_finalize_kernel(double *x0, const double *x1, long sy, long sz, int n1, int n2, const int *where) {
+// zero_only: the buffers have traded places, planes with where == 1 are already in x0
+__global__ void mg_finalize_kernel(double *x0, const double *x1, long sy, long sz, int n1, int n2, const int *where, int zero_only) {
   const int q = blockIdx.z, w = where[q];
-  if (w == 0) return;
+  if (w == 0 || (zero_only && w == 1)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i > n1 || j > n2) return;
   const long o = (long)(q + 1) * sz + i + sy * j;
@@ -1440,13 +1441,22 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
   {
     ProfScope ps(ctx, PC_MG_COARSE);
     MGLevel &L = *S.levels[0];
+    // With the ping-pong buffers every converged plane ends in the second buffer (the stopping test
+    // follows a down kernel).  One process: the buffers trade places and only planes with a zero
+    // right-hand side are written (x = 0), instead of a copy of the whole solution (16 B per point per
+    // solve); the caller re-points the transform at the new array (MGSolver::swapped).  Several
+    // processes: peers hold the address of the first buffer, so the solution is copied into it.
+    static const bool no_swap = getenv("SNAC_MG_SWAP") && atoi(getenv("SNAC_MG_SWAP")) == 0;
+    const bool swap = in_alt && ctx.comm.nproc == 1 && !no_swap;
     for (size_t lb = 0; lb < L.boxes.size(); ++lb) {
       const Grid3 &g = L.boxes[lb].g;
       dim3 blk(64, 4, 1), grd((g.n[0] + 63) / 64, (g.n[1] + 3) / 4, nq);
+      if (swap) std::swap(L.boxes[lb].xp, S.x1[lb].p);
       mg_finalize_kernel<<<grd, blk, 0, ctx.stream>>>(cy.xbuf(0, (int)lb, 0), in_alt ? cy.xbuf(0, (int)lb, 1) : cy.xbuf(0, (int)lb, 0),
-                                                      g.sy, g.sz, g.n[0], g.n[1], S.d_where);
+                                                      g.sy, g.sz, g.n[0], g.n[1], S.d_where, swap ? 1 : 0);
       ctx.launches++;
     }
+    if (swap) S.swapped = true;
   }
 }
 

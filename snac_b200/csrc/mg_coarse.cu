@@ -17,6 +17,10 @@
 //   b~_c(I,J) = sum_children (w1_i / W1_I)(w2_j / W2_J) r~(i,j),   W = width of the coarse cell.
 #include "common.h"
 
+#ifndef SNAC_COARSE_WARP_CELLS
+#define SNAC_COARSE_WARP_CELLS 256   // levels with at most this many cells are run by warp 0 alone
+#endif
+
 namespace snac {
 
 namespace {
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   const int nbot = s_nbot;
   // first level left to warp 0 alone (at most 256 cells); level 0 always belongs to the CTA
   int lsw = nlev;
-  while (lsw > 1 && lv[lsw - 1].n1 * lv[lsw - 1].n2 <= 256) --lsw;
+  while (lsw > 1 && lv[lsw - 1].n1 * lv[lsw - 1].n2 <= SNAC_COARSE_WARP_CELLS) --lsw;
   TS();
   double r2 = 0.0, b2 = 0.0;
   // ---- down leg, CTA-wide levels

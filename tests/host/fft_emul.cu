@@ -21,14 +21,14 @@ static void emulate(const R2RArgs &a, int dir, long ntiles) {
       for (int tid = 0; tid < P::THREADS; ++tid) fn(radix::thread_of(a, tid, P::THREADS, (int)tile));
     };
     if (dir > 0) {
-      if (a.fill.on) phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, true>(a, Z.data(), T); });
-      else phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, false>(a, Z.data(), T); });
+      if (a.fill.on) phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, true, true>(a, Z.data(), T); });
+      else phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, false, true>(a, Z.data(), T); });
       phase([&](const radix::Thread &T) { radix::run_pass<R1, R2, false>(a, Z.data(), T); });
-      phase([&](const radix::Thread &T) { radix::fwd_untangle<R1, R2>(a, Z.data(), T); });
+      phase([&](const radix::Thread &T) { radix::fwd_untangle<R1, R2, true>(a, Z.data(), T); });
     } else {
-      phase([&](const radix::Thread &T) { radix::bwd_tangle<R1, R2>(a, Z.data(), T); });
+      phase([&](const radix::Thread &T) { radix::bwd_tangle<R1, R2, true>(a, Z.data(), T); });
       phase([&](const radix::Thread &T) { radix::run_pass<R1, R2, true>(a, Z.data(), T); });
-      phase([&](const radix::Thread &T) { radix::bwd_pass2<R1, R2>(a, Z.data(), T); });
+      phase([&](const radix::Thread &T) { radix::bwd_pass2<R1, R2, true>(a, Z.data(), T); });
     }
   }
 }
