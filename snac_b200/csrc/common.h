@@ -359,6 +359,12 @@ struct MGSolver {
   void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched, int max_levels = 24);
   void solve(Ctx &ctx);
   const Grid3 &grid0(int lb) const { return levels[0]->boxes[lb].g; }
+  // Initial guess per key (one process, plane-local path): the solution of the last solve with the same key
+  // -- the same RK sub-step one time step earlier -- is a closer guess than the previous sub-step's; each
+  // key keeps its own level-0 array and the solve starts by making it the current one (pointer exchange).
+  std::vector<Field3> key_store[HIST_KEYS];   // arrays of the keys that are not current, per box
+  std::vector<double *> key_ptr[HIST_KEYS];
+  int cur_key = 0;
   bool swapped = false;            // the level-0 iterate moved to the other buffer during the last solve (plane-local path)
   double *xcur(int lb) const { return levels[0]->boxes[lb].xp; }
   double *bcur(int lb) const { return levels[0]->boxes[lb].bp; }

@@ -1402,6 +1402,29 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
     if (i < prev_n) return std::min(nq, std::max(1, prev[i] + prev[i] / 8 + 1));
     return std::max(1, polled);
   };
+  {   // initial guess: the last solution of this key (see MGSolver::key_store)
+    static const bool per_key = !(getenv("SNAC_MG_GUESS_PER_KEY") && atoi(getenv("SNAC_MG_GUESS_PER_KEY")) == 0);
+    if (per_key && in_alt && ctx.comm.nproc == 1 && key != S.cur_key) {
+      MGLevel &L0 = *S.levels[0];
+      const size_t nb = L0.boxes.size();
+      for (int k : {key, S.cur_key})
+        if (S.key_ptr[k].size() != nb) S.key_ptr[k].assign(nb, nullptr);
+      if (S.key_store[key].size() != nb) {   // first solve with this key: its own array, zero guess
+        S.key_store[key].resize(nb);
+        for (size_t lb = 0; lb < nb; ++lb) {
+          S.key_store[key][lb].alloc(L0.boxes[lb].g);
+          S.key_ptr[key][lb] = S.key_store[key][lb].p;
+        }
+      }
+      for (size_t lb = 0; lb < nb; ++lb) {
+        S.key_ptr[S.cur_key][lb] = L0.boxes[lb].xp;   // the current array goes to rest with the solution of its key
+        L0.boxes[lb].xp = S.key_ptr[key][lb];
+        S.key_ptr[key][lb] = nullptr;
+      }
+      S.cur_key = key;
+      S.swapped = true;
+    }
+  }
   bool first = true;
   for (;;) {
     // cycles enqueued before the host looks at the counter: as many as the last solve needed, then two at a time
