@@ -23,13 +23,13 @@ struct MomArgs {
 
 // Block shape and register budget, measured on TGV-256 (B200): 64x4 threads / 80 registers 1.40 ms per
 // step, 32x8 and 128x2 the same, 64x2 / 80 registers 1.33 ms, 64x2 / 72 registers (7 CTAs per SM,
-// 36 bytes of spills) 1.32 ms; 64x4 squeezed into 64 registers 1.58 ms.
+// 36 bytes of spills) 1.31 ms, 64x1 / 72 registers 1.29 ms; 64x4 squeezed into 64 registers 1.58 ms.
 #ifndef SNAC_MOM_MINB
-#define SNAC_MOM_MINB 7
+#define SNAC_MOM_MINB 14
 #endif
 #ifndef SNAC_MOM_BX
 #define SNAC_MOM_BX 64
-#define SNAC_MOM_BY 2
+#define SNAC_MOM_BY 1
 #endif
 template <bool IMPDIFF, bool BUOY, bool FIRST>
 __global__ void __launch_bounds__(SNAC_MOM_BX * SNAC_MOM_BY, SNAC_MOM_MINB) rk_mom_kernel(const MomArgs a) {
