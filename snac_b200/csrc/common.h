@@ -472,6 +472,7 @@ struct Ctx {
   std::string err;
   // exchanges / BC fills
   Exchange ex_uvw[2], ex_p, ex_pp;
+  Exchange ex_uvwp[2];     // u,v,w,p together (end of a sub-step)
   FaceFill bc_uvw[2][2];   // [parity][is_correc]
   FaceFill bc_inflow[2][2];
   bool has_inflow = false, inflow_dirty = false;
