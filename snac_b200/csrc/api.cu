@@ -274,7 +274,7 @@ static void commit(Ctx &ctx) {
       int pd[2], q = 0;
       for (int d = 0; d < 3; ++d) if (d != fa) pd[q++] = d;
       Grid3 sg = Grid3::make(B.hi_g[pd[0]] - B.lo_g[pd[0]] + 1, B.hi_g[pd[1]] - B.lo_g[pd[1]] + 1, std::max(ctx.q1 - ctx.q0, 1));
-      bytes += 2 * (sg.alloc_elems() * sizeof(double) + 256);
+      bytes += 5 * (sg.alloc_elems() * sizeof(double) + 256);   // right-hand side + the four arrays of MGSolver::xslot
     }
     ctx.comm.init(ctx.prm.nproc, ctx.prm.myproc, bytes);
   }
@@ -365,6 +365,9 @@ static void commit(Ctx &ctx) {
           Grid3 sg = Grid3::make(s.n[0], s.n[1], std::max(s.n[2], 1));
           s.x = ctx.comm.alloc(sg.alloc_elems(), B.id, AK_SLAB_X) + 15;
           s.b = ctx.comm.alloc(sg.alloc_elems(), B.id, AK_SLAB_B) + 15;
+          s.xalt[0] = ctx.comm.alloc(sg.alloc_elems(), B.id, AK_SLAB_X1) + 15;
+          s.xalt[1] = ctx.comm.alloc(sg.alloc_elems(), B.id, AK_SLAB_K1) + 15;
+          s.xalt[2] = ctx.comm.alloc(sg.alloc_elems(), B.id, AK_SLAB_K2) + 15;
         }
       }
       ctx.blocks_lo.clear();
@@ -473,6 +476,11 @@ static void finish_setup(Ctx &ctx) {
         double *xb, *bb;
         if (p == ctx.comm.me) { xb = S.xcur(bi); bb = S.bcur(bi); }
         else { xb = ctx.comm.remote(p, b.info.block, AK_SLAB_X) + 15; bb = ctx.comm.remote(p, b.info.block, AK_SLAB_B) + 15; }
+        // every array the owner's iterate can move to (the owner's own ones are looked up when they are needed)
+        static const int slot_keys[4] = {AK_SLAB_X, AK_SLAB_X1, AK_SLAB_K1, AK_SLAB_K2};
+        for (int sl = 0; sl < 4; ++sl)
+          R.xs[p][sl] = (p == ctx.comm.me || ctx.comm.nproc == 1) ? nullptr
+                        : ctx.comm.remote(p, b.info.block, slot_keys[sl]) + 15 + off - (q_is_cyclic(ctx) ? 0 : (long)q0 * sg.st(2));
         // chunks: the wavenumber index is absolute in the kernels, shift by the slab origin; cyclic: the
         // kernels divide the index by the number of processes themselves
         const long shift = q_is_cyclic(ctx) ? 0 : (long)q0 * sg.st(2);
@@ -681,12 +689,22 @@ static void do_fft(Ctx &ctx, int dir, double dtrk = 0.0) {
 }
 static void do_solve(Ctx &ctx) {
   ctx.psolver.solve(ctx);
-  if (ctx.psolver.swapped) {   // one process: the solution array traded places with the solver's second buffer
+  if (ctx.psolver.swapped) {   // the solution lives in another of the solver's arrays now: here and, alike, on every peer
+    MGSolver &S = ctx.psolver;
     for (int lb = 0; lb < (int)ctx.boxes.size(); ++lb) {
       FFTRoute &R = ctx.route[lb];
-      R.x[0] = ctx.psolver.xcur(ctx.block_index[ctx.boxes[lb]->info.block]) + R.off;
+      const int bi = ctx.block_index[ctx.boxes[lb]->info.block];
+      for (int p = 0; p < std::max(R.nsplit, 1); ++p) {
+        if (p == ctx.comm.me || ctx.comm.nproc == 1) {
+          int q0, q1;
+          q_range(ctx, ctx.nq, ctx.comm.me, q0, q1);
+          R.x[p] = S.xcur(bi) + R.off - (q_is_cyclic(ctx) || ctx.comm.nproc == 1 ? 0 : (long)q0 * S.grid0(bi).st(2));
+        } else {
+          R.x[p] = R.xs[p][S.slot_primary];
+        }
+      }
     }
-    ctx.psolver.swapped = false;
+    S.swapped = false;
   }
   // batched: the peers read this process' solution slab in the backward transform
   if (ctx.prm.fft_axis > 0) ctx.comm.handshake(ctx, CH_SOLVED, ~0u);

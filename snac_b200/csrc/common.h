@@ -157,6 +157,7 @@ struct FFTRoute {
   double *x[16] = {nullptr}, *b[16] = {nullptr};
   int chunk = 1, nsplit = 1;
   long off = 0;                    // first cell of the box inside its block's solver array
+  double *xs[16][4] = {{nullptr}};  // x[p] for each of the arrays the owner's iterate can live in (MGSolver::xslot)
   bool cyclic = false;             // wavenumber q is solved by process q mod nproc (else: consecutive chunks)
 };
 
@@ -314,6 +315,7 @@ struct SBox {
   std::vector<double> d1[3], d2[3]; // ghosted spacings: between unknowns / cell widths
   std::vector<double> lam;          // ghosted eigenvalues/dl^2 along direction 2 (batched only)
   double *x = nullptr, *b = nullptr; // level-0 arrays if they alias context fields (3-D solve)
+  double *xalt[3] = {nullptr, nullptr, nullptr};   // several processes: arena arrays for MGSolver::xslot[..][1..3]
   long sy = 0, sz = 0;              // their strides when they differ from Grid3::make(n) (shortened staggered ranges)
   int qqq[3] = {0, 0, 0};           // 1: unknowns staggered along that direction (src/solver.f90:66-67)
 };
@@ -359,11 +361,19 @@ struct MGSolver {
   void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched, int max_levels = 24);
   void solve(Ctx &ctx);
   const Grid3 &grid0(int lb) const { return levels[0]->boxes[lb].g; }
-  // Initial guess per key (one process, plane-local path): the solution of the last solve with the same key
-  // -- the same RK sub-step one time step earlier -- is a closer guess than the previous sub-step's; each
-  // key keeps its own level-0 array and the solve starts by making it the current one (pointer exchange).
-  std::vector<Field3> key_store[HIST_KEYS];   // arrays of the keys that are not current, per box
-  std::vector<double *> key_ptr[HIST_KEYS];
+  // Plane-local path: four arrays can hold the level-0 iterate of a box -- the current one, the ping-pong
+  // partner of the fused kernels, and one per key that is not current.  Initial guess per key: the
+  // solution of the last solve with the same key (the same RK sub-step one time step earlier) is a
+  // closer guess than the previous sub-step's, so each key keeps its own array and a solve starts by
+  // making it the current one.  Every converged plane ends in the ping-pong partner, so the two trade
+  // places at the end of a solve instead of a copy.  Both are exchanges of slot numbers; with several
+  // processes the arrays live in the arena and every process applies the same exchanges to its
+  // peers' addresses (the sequence of solves and keys is the same everywhere).
+  static constexpr int NSLOT = 4;
+  std::vector<std::array<double *, NSLOT>> xslot;   // per box
+  std::vector<Field3> slot_own[NSLOT];               // arrays owned here (one process; allocated on first use)
+  int slot_primary = 0, slot_scratch = 1;
+  int slot_key[HIST_KEYS] = {-1, 2, 3, -1};          // where the array of a key rests (-1: it is the current one / none)
   int cur_key = 0;
   bool swapped = false;            // the level-0 iterate moved to the other buffer during the last solve (plane-local path)
   double *xcur(int lb) const { return levels[0]->boxes[lb].xp; }
@@ -405,7 +415,8 @@ struct Box {
 constexpr int MAXPROC = 16;
 enum CommChannel : int { CH_READY = 0, CH_ARRIVED = 1, CH_FFT = 2, CH_SOLVED = 3, CH_REDUCE = 4, CH_COUNT = 5 };
 enum ArenaKey : int {   // exported arrays: per box (rank) or per block
-  AK_U0 = 0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P, AK_PP, AK_S0 /* .. AK_S0+7 */, AK_SLAB_X = 24, AK_SLAB_B = 25
+  AK_U0 = 0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P, AK_PP, AK_S0 /* .. AK_S0+7 */, AK_SLAB_X = 24, AK_SLAB_B = 25,
+  AK_SLAB_X1 = 26, AK_SLAB_K1 = 27, AK_SLAB_K2 = 28   // the other arrays that can hold the solver's level-0 iterate (MGSolver::xslot)
 };
 struct ArenaRec { int id, key; long long off; };   // id: box rank or block; off: bytes from the arena base
 constexpr int MAXREC = 1024;

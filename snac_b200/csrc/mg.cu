@@ -1119,7 +1119,19 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
       x1.clear();
       x1.resize((size_t)ls * nl);
       for (int l = 0; l < ls; ++l)
-        for (int lb = 0; lb < nl; ++lb) x1[(size_t)l * nl + lb].alloc(levels[l]->boxes[lb].g);
+        for (int lb = 0; lb < nl; ++lb) {
+          if (l == 0 && sboxes[lb].xalt[0]) x1[lb].p = sboxes[lb].xalt[0];   // arena memory (several processes)
+          else x1[(size_t)l * nl + lb].alloc(levels[l]->boxes[lb].g);
+        }
+      xslot.assign(nl, {nullptr, nullptr, nullptr, nullptr});
+      for (int lb = 0; lb < nl; ++lb) {
+        xslot[lb][0] = levels[0]->boxes[lb].xp;
+        xslot[lb][1] = ls > 0 ? x1[lb].p : nullptr;
+        xslot[lb][2] = sboxes[lb].xalt[1];
+        xslot[lb][3] = sboxes[lb].xalt[2];
+      }
+      slot_primary = 0; slot_scratch = 1; cur_key = 0;
+      slot_key[0] = -1; slot_key[1] = 2; slot_key[2] = 3; slot_key[3] = -1;
     }
   }
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
@@ -1402,25 +1414,23 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
     if (i < prev_n) return std::min(nq, std::max(1, prev[i] + prev[i] / 8 + 1));
     return std::max(1, polled);
   };
-  {   // initial guess: the last solution of this key (see MGSolver::key_store)
+  {   // initial guess: the last solution of this key (see MGSolver::xslot)
     static const bool per_key = !(getenv("SNAC_MG_GUESS_PER_KEY") && atoi(getenv("SNAC_MG_GUESS_PER_KEY")) == 0);
-    if (per_key && in_alt && ctx.comm.nproc == 1 && key != S.cur_key) {
+    if (per_key && in_alt && key != S.cur_key && S.slot_key[key] >= 0) {
       MGLevel &L0 = *S.levels[0];
-      const size_t nb = L0.boxes.size();
-      for (int k : {key, S.cur_key})
-        if (S.key_ptr[k].size() != nb) S.key_ptr[k].assign(nb, nullptr);
-      if (S.key_store[key].size() != nb) {   // first solve with this key: its own array, zero guess
-        S.key_store[key].resize(nb);
-        for (size_t lb = 0; lb < nb; ++lb) {
-          S.key_store[key][lb].alloc(L0.boxes[lb].g);
-          S.key_ptr[key][lb] = S.key_store[key][lb].p;
+      const int snew = S.slot_key[key];
+      for (size_t lb = 0; lb < L0.boxes.size(); ++lb) {
+        if (!S.xslot[lb][snew]) {   // one process, first solve with this key: its own array, zero guess
+          if (ctx.comm.nproc > 1) throw Error("solver: the per-key iterate arrays were not placed in the arena");
+          if (S.slot_own[snew].size() != L0.boxes.size()) S.slot_own[snew].resize(L0.boxes.size());
+          S.slot_own[snew][lb].alloc(L0.boxes[lb].g);
+          S.xslot[lb][snew] = S.slot_own[snew][lb].p;
         }
+        L0.boxes[lb].xp = S.xslot[lb][snew];
       }
-      for (size_t lb = 0; lb < nb; ++lb) {
-        S.key_ptr[S.cur_key][lb] = L0.boxes[lb].xp;   // the current array goes to rest with the solution of its key
-        L0.boxes[lb].xp = S.key_ptr[key][lb];
-        S.key_ptr[key][lb] = nullptr;
-      }
+      S.slot_key[S.cur_key] = S.slot_primary;   // the current array goes to rest with the solution of its key
+      S.slot_primary = snew;
+      S.slot_key[key] = -1;
       S.cur_key = key;
       S.swapped = true;
     }
@@ -1465,16 +1475,16 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
     ProfScope ps(ctx, PC_MG_COARSE);
     MGLevel &L = *S.levels[0];
     // With the ping-pong buffers every converged plane ends in the second buffer (the stopping test
-    // follows a down kernel).  One process: the buffers trade places and only planes with a zero
-    // right-hand side are written (x = 0), instead of a copy of the whole solution (16 B per point per
-    // solve); the caller re-points the transform at the new array (MGSolver::swapped).  Several
-    // processes: peers hold the address of the first buffer, so the solution is copied into it.
+    // follows a down kernel): the buffers trade places and only planes with a zero right-hand side are
+    // written (x = 0), instead of a copy of the whole solution (16 B per point per solve); the caller
+    // re-points the transform at the new array, its own and its peers' (MGSolver::swapped, xslot).
     static const bool no_swap = getenv("SNAC_MG_SWAP") && atoi(getenv("SNAC_MG_SWAP")) == 0;
-    const bool swap = in_alt && ctx.comm.nproc == 1 && !no_swap;
+    const bool swap = in_alt && !no_swap;
+    if (swap) std::swap(S.slot_primary, S.slot_scratch);
     for (size_t lb = 0; lb < L.boxes.size(); ++lb) {
       const Grid3 &g = L.boxes[lb].g;
       dim3 blk(64, 4, 1), grd((g.n[0] + 63) / 64, (g.n[1] + 3) / 4, nq);
-      if (swap) std::swap(L.boxes[lb].xp, S.x1[lb].p);
+      if (swap) { L.boxes[lb].xp = S.xslot[lb][S.slot_primary]; S.x1[lb].p = S.xslot[lb][S.slot_scratch]; }
       mg_finalize_kernel<<<grd, blk, 0, ctx.stream>>>(cy.xbuf(0, (int)lb, 0), in_alt ? cy.xbuf(0, (int)lb, 1) : cy.xbuf(0, (int)lb, 0),
                                                       g.sy, g.sz, g.n[0], g.n[1], S.d_where, swap ? 1 : 0);
       ctx.launches++;
