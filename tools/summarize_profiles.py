@@ -38,9 +38,9 @@ for r in rows[h + 1:]:
 shutil.copy(src, os.path.join(out, f"{tag}_ncu_launches.csv"))
 total = sum(t for _, t in tot.values())
 with open(os.path.join(out, f"{tag}_ncu_launches_summary.md"), "w") as f:
-    f.write(f"# ncu launch list of `bench.py --steps 2 --warmup 3` (TGV 256^3, 1 GPU), {sum(n for n, _ in tot.values())} launches\n\n")
+    f.write(f"# ncu launch list of `bench.py --steps 2 --warmup 4` (TGV 256^3, 1 GPU), {sum(n for n, _ in tot.values())} launches\n\n")
     f.write("Command (profiling recipe): `ncu --metrics gpu__time_duration.sum --clock-control none -s 420 -c 400 --csv "
-            "--log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1`\n\n")
+            "--log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 4 --no-cpu --e2e-steps 1`\n\n")
     f.write("Per-launch times are cold-cache and serialised: compare shares, not absolutes.\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
@@ -61,7 +61,7 @@ traffic = {}
 with open(os.path.join(out, f"{tag}_ncu_full_summary.md"), "w") as f:
     f.write(f"# ncu --set full capture ({tag}), TGV 256^3, 1 GPU\n\n")
     f.write("`ncu --set full --clock-control none --import-source on -k regex:\"mg_ring|mg_coarse|rk_mom|r2r_radix|correc|fillps\" "
-            "-s 40 -c 22 python bench.py --steps 1 --warmup 2 --no-cpu --e2e-steps 1`\n\n")
+            "-s 60 -c 20 python bench.py --steps 1 --warmup 4 --no-cpu --e2e-steps 1`\n\n")
     f.write("| kernel | grid | " + " | ".join(t for _, t in cols) + " |\n|---|---|" + "---|" * len(cols) + "\n")
     for r in data:
         name = short(r[ix["Kernel Name"]])
