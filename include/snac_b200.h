@@ -153,6 +153,14 @@ SNAC_API int snac_correc(snac_handle *h, double dtrk);                   /* corr
 SNAC_API int snac_updt_pressure(snac_handle *h, double alpha);           /* updt_pressure, src/updt_pressure.f90:7-47 */
 SNAC_API int snac_chkdt(snac_handle *h, double *dt_cfl);                 /* chkdt, src/chkdt.f90:8-56 (global) */
 SNAC_API int snac_chkdiv(snac_handle *h, double *divtot, double *divmax);/* chkdiv, src/chkdiv.f90:8-44 (global) */
+/* Plane averages of the output routines on the device: the contribution of box `rank` (the sum over the boxes of a
+ * block, MPI_ALLREDUCE over comm_block in the reference, and the text file stay with the host).  idir = 0..2; the
+ * weights are the ghosted 1-D spacing arrays the reference passes (index lo-1:hi+1) for the two averaged directions
+ * a < b (out1d) or for idir (out2d); scale = 1/(l_a l_b) resp. 1/l_idir.
+ *   out1d, src/output.f90:34-133:  p1d(t)   = sum_{a,b} p(a,b,t) wa(a) wb(b) scale     -> n[idir] values
+ *   out2d, src/output.f90:135-225: p2d(a,b) = sum_t p(a,b,t) w(t) scale                -> n[a]*n[b] values, a fastest */
+SNAC_API int snac_out1d(snac_handle *h, int rank, int field, int idir, const double *wa, const double *wb, double scale, double *p1d);
+SNAC_API int snac_out2d(snac_handle *h, int rank, int field, int idir, const double *w, double scale, double *p2d);
 
 /* ---- coarse-grained entry point: the whole `do irk=1,3` body, src/main.f90:906-1033 -------- */
 SNAC_API int snac_step(snac_handle *h, double dt);

@@ -1040,6 +1040,21 @@ int snac_chkdt(snac_handle *h, double *dt_cfl) {
     *dt_cfl = dtmax;
   })
 }
+// out1d / out2d (src/output.f90:34-225): contribution of box `rank`, see output.cu
+static void out_reduce(Ctx &ctx, int rank, int field, int which, int idir, const double *wa, const double *wb, double scale, double *out) {
+  Box &b = ctx.box_of_rank(rank);
+  bool alias = false;
+  Field3 *f = field_of(ctx, b, field, alias);
+  if (!f || !f->p) throw Error("out1d/out2d: unknown field");
+  if (!wa || (which == 1 && !wb) || !out) throw Error("out1d/out2d: null argument");
+  launch_out_reduce(ctx, b.g, f->p, which, idir, wa, wb, scale, out);
+}
+int snac_out1d(snac_handle *h, int rank, int field, int idir, const double *wa, const double *wb, double scale, double *p1d) {
+  SNAC_TRY(h, out_reduce(h->ctx, rank, field, 1, idir, wa, wb, scale, p1d))
+}
+int snac_out2d(snac_handle *h, int rank, int field, int idir, const double *w, double scale, double *p2d) {
+  SNAC_TRY(h, out_reduce(h->ctx, rank, field, 2, idir, w, nullptr, scale, p2d))
+}
 int snac_chkdiv(snac_handle *h, double *divtot, double *divmax) {
   SNAC_TRY(h, {
     double r[3];

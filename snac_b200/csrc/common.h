@@ -528,6 +528,8 @@ void launch_fillps(Ctx &ctx, Box &b, double dtrk);
 void launch_fillps_bc(Ctx &ctx, Box &b, double dtrk);
 void launch_updt_rhs(Ctx &ctx, Box &b);
 void launch_correc_updt(Ctx &ctx, Box &b, double dtrk, double alpha, bool do_correc, bool do_updt);
+void launch_out_reduce(Ctx &ctx, const Grid3 &g, const double *field, int which, int idir, const double *wa, const double *wb,
+                       double scale, double *host);   // output.cu: out1d / out2d plane averages of one box
 void launch_chk(Ctx &ctx, Box &b, double *d_out /* [4]: dti_max, divtot, divmax, - */);
 void launch_helm_rhs(Ctx &ctx, Box &b, const double *fld, const double *const wq[3], const double cb[3][2], const int nhi[3],
                      double alphai);

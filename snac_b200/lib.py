@@ -80,6 +80,8 @@ EXPORTS = {
     "snac_updt_pressure": (C.c_int, [C.c_void_p, C.c_double]),
     "snac_chkdt": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "snac_chkdiv": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "snac_out1d": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "snac_out2d": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p]),
     "snac_step": (C.c_int, [C.c_void_p, C.c_double]),
     "snac_solver_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "snac_solver_mean_iters": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

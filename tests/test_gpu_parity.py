@@ -335,6 +335,49 @@ def test_inflow_steps_match_oracle(tmp_path, fa):
     assert divmax < 1e-9
 
 
+@pytest.mark.parametrize("kind,fa", [("channel", 2), ("duct", 1)])
+def test_out1d_out2d_on_the_device(tmp_path, kind, fa):
+    """`out1d` / `out2d` (src/output.f90:34-225) evaluated by snac_out1d / snac_out2d against the reference's
+    loops restated in numpy on the downloaded fields: stretched grid, several boxes per block, several blocks."""
+    from snac_b200 import output
+    from snac_b200.sim import Simulation
+    case = cases.make(kind, str(tmp_path / "run"), fft_axis=fa)
+    g = Simulation(case)
+    g.set_fields(cases.random_fields(case, seed=5))
+    I = (slice(1, -1),) * 3
+    for ib, blk in enumerate(case.params.blocks):
+        l = np.asarray(blk.lmax, float) - np.asarray(blk.lmin, float)
+        boxes = [b for b in case.world.boxes if b.block == ib]
+        lo_g = np.min([b.lo for b in boxes], axis=0)
+        for field, stag in ((L.FIELD_U, 0), (L.FIELD_W, 2), (L.FIELD_P, -1)):
+            for idir in range(3):
+                a, b_ = [d for d in range(3) if d != idir]
+                ref1 = np.zeros(int(blk.ng[idir]))
+                ref2 = np.zeros((int(blk.ng[a]), int(blk.ng[b_])))
+                for box in boxes:
+                    gr = case.grids[box.rank]
+                    w = [(gr.dc(d) if d == stag else gr.df(d))[1:-1] for d in range(3)]
+                    p = g.download(box.rank, field)[I]
+                    wgt = [w[d].reshape([-1 if e == d else 1 for e in range(3)]) for d in range(3)]
+                    s = [int(box.lo[d] - lo_g[d]) for d in range(3)]
+                    ref1[s[idir]:s[idir] + p.shape[idir]] += (p * wgt[a] * wgt[b_]).sum(axis=(a, b_)) / (l[a] * l[b_])
+                    ref2[s[a]:s[a] + p.shape[a], s[b_]:s[b_] + p.shape[b_]] += (p * wgt[idir]).sum(axis=idir) / l[idir]
+                got1 = output.block_profile(g, ib, field, idir, stag)
+                got2 = output.block_average(g, ib, field, idir, stag)
+                assert np.max(np.abs(got1 - ref1)) <= 1e-13 * max(np.max(np.abs(ref1)), 1e-3)
+                assert np.max(np.abs(got2 - ref2)) <= 1e-13 * max(np.max(np.abs(ref2)), 1e-3)
+    # the files of the out1d.h90 hook: 12 per block, two columns in E15.7
+    data = str(tmp_path / "data")
+    output.out1d_hook(g, data, "0000010")
+    fn = os.path.join(data, "umean_z_fld_0000010_b_001.out")
+    tab = np.loadtxt(fn)
+    assert tab.shape == (int(case.params.blocks[0].ng[2]), 2)
+    assert np.allclose(tab[:, 0], case.bgrids[0][2].rc[1:-1], rtol=6e-7, atol=1e-12)   # E15.7: seven significant digits
+    assert np.allclose(tab[:, 1], output.block_profile(g, 0, L.FIELD_U, 2, 0), rtol=6e-7, atol=1e-9)
+    assert len(os.listdir(data)) == 12 * len(case.params.blocks)
+    g.close()
+
+
 def test_checkpoint_restart_in_the_reference_layout(tmp_path):
     """fld_b_###_{u,v,w,p}.bin written from the device fields (snac_b200/load.py; src/load.f90:84-187,
     src/main.f90:1090-1117), restart from them (src/main.f90:542-556): the restarted run continues like the
