@@ -281,6 +281,7 @@ struct CoarseArgs {
   double *norms;             // only when the top level is level 0
   double xscale;             // factor applied to xin
   int nq, want_b, npre, npost, nbot;
+  int npre_low, npost_low;   // sweeps per leg on the levels below the kernel's top level
   int adaptive;              // per-wavenumber depth of the hierarchy (mg_coarse.cu)
   const int *active;
 };

@@ -1322,6 +1322,7 @@ struct Cycle {
       a.xscale = (ls == 0 && want_b) ? S.guess_scale : 1.0;
       a.nq = S.nq; a.want_b = want_b ? 1 : 0;
       a.npre = npre; a.npost = npost; a.nbot = nbot;
+      a.npre_low = npre; a.npost_low = npost;
       {
         static const bool adapt = !(getenv("SNAC_MG_COARSE_ADAPT") && atoi(getenv("SNAC_MG_COARSE_ADAPT")) == 0);
         a.adaptive = (ls > 0 && adapt) ? 1 : 0;
@@ -1330,7 +1331,9 @@ struct Cycle {
         static const int csw = getenv("SNAC_MG_COARSE_NSW") ? atoi(getenv("SNAC_MG_COARSE_NSW")) : 0;
         static const int cml = getenv("SNAC_MG_COARSE_MAXLEV") ? atoi(getenv("SNAC_MG_COARSE_MAXLEV")) : 0;
         static const int cnb = getenv("SNAC_MG_COARSE_NBOT") ? atoi(getenv("SNAC_MG_COARSE_NBOT")) : 0;
-        if (csw > 0) a.npre = a.npost = csw;
+        if (csw > 0) a.npre = a.npost = a.npre_low = a.npost_low = csw;
+        static const int clo = getenv("SNAC_MG_COARSE_NSW_LOW") ? atoi(getenv("SNAC_MG_COARSE_NSW_LOW")) : 0;
+        if (clo > 0) a.npre_low = a.npost_low = clo;
         if (cml > 0) a.nlev = std::min(a.nlev, cml);
         if (cnb > 0) a.nbot = cnb;
       }

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   // ---- down leg, CTA-wide levels
   for (int l = 0; l < lsw - 1; ++l) {
     const CLev F = lv[l], C = lv[l + 1];
-    c_down(sm, F, C, lam, a.npre, GB, l == 0 && a.norms, r2, b2);
+    c_down(sm, F, C, lam, l == 0 ? a.npre : a.npre_low, GB, l == 0 && a.norms, r2, b2);
     TS();
   }
   // ---- from level lsw-1 down: restriction into the first small level by the CTA, then warp 0 runs
@@ -378,27 +378,27 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   if (lsw < nlev) {
     {
       const CLev F = lv[lsw - 1], C = lv[lsw];
-      c_down(sm, F, C, lam, a.npre, GB, lsw == 1 && a.norms, r2, b2);
+      c_down(sm, F, C, lam, lsw == 1 ? a.npre : a.npre_low, GB, lsw == 1 && a.norms, r2, b2);
     }
     TS();
     if (threadIdx.x < 32) {
       for (int l = lsw; l < nlev - 1; ++l) {
         const CLev F = lv[l], C = lv[l + 1];
-        c_down(sm, F, C, lam, a.npre, GW, false, r2, b2);
+        c_down(sm, F, C, lam, a.npre_low, GW, false, r2, b2);
       }
       const CLev B = lv[nlev - 1];
       const int ns = min(nbot, B.n1 * B.n2);   // a 1 x 1 level is solved by one update
       for (int s = 0; s < ns; ++s) { c_sweep(sm, B, 0, lam, GW); c_sweep(sm, B, 1, lam, GW); }
       for (int l = nlev - 2; l >= lsw; --l) {
         const CLev F = lv[l], C = lv[l + 1];
-        c_up(sm, F, C, lam, a.npost, GW);
+        c_up(sm, F, C, lam, a.npost_low, GW);
       }
     }
     __syncthreads();
     TS();
     {
       const CLev F = lv[lsw - 1], C = lv[lsw];
-      c_up(sm, F, C, lam, a.npost, GB);
+      c_up(sm, F, C, lam, lsw == 1 ? a.npost : a.npost_low, GB);
     }
     TS();
   } else {   // the coarsest level belongs to the CTA (a single-level or all-large hierarchy)
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(1024) mg_coarse_kernel(const CoarseArgs a) {
   // ---- up leg, CTA-wide levels
   for (int l = lsw - 2; l >= 0; --l) {
     const CLev F = lv[l], C = lv[l + 1];
-    c_up(sm, F, C, lam, a.npost, GB);
+    c_up(sm, F, C, lam, l == 0 ? a.npost : a.npost_low, GB);
     TS();
   }
   // ---- result
