@@ -269,7 +269,10 @@ static void commit(Ctx &ctx) {
   if (ctx.comm.nproc > 1) {
     if (!batched) throw Error("a 3-D solve (fft_axis = 0) distributed over several processes is not available in this build");
     size_t bytes = 0;
-    for (auto &bp : ctx.boxes) bytes += (size_t)(8 + ctx.prm.nscal) * (bp->g.alloc_elems() * sizeof(double) + 256);
+    for (auto &bp : ctx.boxes) {
+      bytes += (size_t)(8 + ctx.prm.nscal) * (bp->g.alloc_elems() * sizeof(double) + 256);
+      bytes += (size_t)2 * (8 + ctx.prm.nscal) * ((size_t)(bp->g.n[1] + 2) * (bp->g.n[2] + 2) * sizeof(double) + 256);   // x-face landing buffers
+    }
     for (BlockInfo &B : blocks) {
       int pd[2], q = 0;
       for (int d = 0; d < 3; ++d) if (d != fa) pd[q++] = d;
@@ -308,6 +311,16 @@ static void commit(Ctx &ctx) {
     for (int s = 0; s < ctx.prm.nscal; ++s) { alloc_field(ctx, b.s[s], b.g, r, AK_S0 + s); b.ds[s].alloc(b.g); }
     if (ctx.prm.nscal > 0) { b.scr0.alloc(b.g); b.scr1.alloc(b.g); }
     compute_bc_rhs(ctx, b);
+    if (ctx.comm.nproc > 1) {   // landing buffers of the x-faces pushed by neighbours on other processes (bound.cu)
+      std::vector<int> fkeys = {AK_U0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P};
+      if (!b.pp_is_po) fkeys.push_back(AK_PP);
+      for (int s = 0; s < ctx.prm.nscal; ++s) fkeys.push_back(AK_S0 + s);
+      for (int ib = 0; ib < 2; ++ib) {
+        const int nbr = b.info.nb[0][ib];
+        if (nbr < 0 || ctx.owner[nbr] == ctx.comm.me) continue;
+        for (int k : fkeys) ctx.comm.alloc((size_t)(b.g.n[1] + 2) * (b.g.n[2] + 2), r, AK_XSTAGE + 2 * k + ib);
+      }
+    }
   }
   // transforms (fftini for the pressure, src/main.f90:735)
   if (batched) {

@@ -7,6 +7,8 @@
 // self-neighbours) and a table of face-fill descriptors live in device memory, built at commit.
 // Directions are processed x, y, z with full ghost extents so that edges and corners propagate
 // exactly as in the reference (src/bound.f90:26-34).
+#include <cstdlib>
+
 #include "common.h"
 
 namespace snac {
@@ -79,7 +81,7 @@ void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::ve
   // box's first/last interior plane is pushed into the neighbour's ghost plane in the peer's arena.
   const int nl = nbs ? (int)nbs->size() : (int)ctx.boxes.size();
   if (fields.size() % nl) throw Error("Exchange::build: field list is not a multiple of the box count");
-  std::vector<CopyOp> ops[3];
+  std::vector<CopyOp> ops[3], unp[3];
   for (int d = 0; d < 3; ++d) mask[d] = 0;
   key0 = (keys && ctx.comm.nproc > 1) ? (*keys)[0] : -1;   // only exchanges of published arrays synchronise with peers
   for (size_t f = 0; f < fields.size() / nl; ++f) {
@@ -112,13 +114,30 @@ void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::ve
             const Grid3 rg = Grid3::make(w.hi[0] - w.lo[0] + 1, w.hi[1] - w.lo[1] + 1, w.hi[2] - w.lo[2] + 1);
             if (rg.n[da] != me.g.n[da] || rg.n[db] != me.g.n[db])
               throw Error("halo exchange: neighbouring boxes are not face-congruent");
-            double *rp = ctx.comm.remote(proc, nbr, (*keys)[f]) + 15;
-            op.ssa = me.g.st(da); op.ssb = me.g.st(db);
-            op.dsa = rg.st(da);   op.dsb = rg.st(db);
             const long sidx = (ib == 0) ? 1 : me.g.n[d];            // my lo / hi interior plane
             const long didx = (ib == 0) ? rg.n[d] + 1 : 0;          // the neighbour's hi / lo ghost plane
+            op.ssa = me.g.st(da); op.ssb = me.g.st(db);
             op.src = me.p + sidx * me.g.st(d);
-            op.dst = rp + didx * rg.st(d);
+            static const bool xstage = !(getenv("SNAC_XFACE_STAGE") && atoi(getenv("SNAC_XFACE_STAGE")) == 0);
+            if (d == 0 && xstage) {
+              // An x-face is one element per row: pushed in place it is (n2+2)(n3+2) separate 8-byte stores
+              // over NVLink.  It is gathered into a dense landing buffer of the neighbour instead (coalesced
+              // remote stores); the neighbour scatters it into its ghost column once the push has arrived.
+              const int fkey = (*keys)[f];
+              op.dst = ctx.comm.remote(proc, nbr, AK_XSTAGE + 2 * fkey + (1 - ib));   // its hi / lo side
+              op.dsa = 1; op.dsb = op.na;
+              CopyOp un;   // my own ghost plane on side ib is filled from my landing buffer of that side
+              un.na = op.na; un.nb = op.nb;
+              un.src = ctx.comm.remote(ctx.comm.me, ctx.boxes[lb]->info.rank, AK_XSTAGE + 2 * fkey + ib);
+              un.ssa = 1; un.ssb = un.na;
+              un.dst = me.p + ((ib == 0) ? 0 : me.g.n[d] + 1) * me.g.st(d);
+              un.dsa = me.g.st(da); un.dsb = me.g.st(db);
+              unp[d].push_back(un);
+            } else {
+              double *rp = ctx.comm.remote(proc, nbr, (*keys)[f]) + 15;
+              op.dsa = rg.st(da);   op.dsb = rg.st(db);
+              op.dst = rp + didx * rg.st(d);
+            }
             mask[d] |= 1u << proc;
           }
           ops[d].push_back(op);
@@ -126,7 +145,7 @@ void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::ve
       }
     }
   }
-  for (int d = 0; d < 3; ++d) local[d].upload(ops[d]);
+  for (int d = 0; d < 3; ++d) { local[d].upload(ops[d]); unpack[d].upload(unp[d]); }
 }
 
 // one direction: wait until the neighbours are done with the ghost cells (they reached the same
@@ -135,6 +154,7 @@ void Exchange::run(Ctx &ctx, int dir) const {
   if (key0 >= 0) ctx.comm.handshake(ctx, CH_READY, mask[dir]);
   launch_copy_ops(ctx, local[dir]);
   if (key0 >= 0) ctx.comm.handshake(ctx, CH_ARRIVED, mask[dir]);
+  launch_copy_ops(ctx, unpack[dir]);
 }
 
 void Exchange::run_all(Ctx &ctx) const {   // x, then y, then z (edges/corners propagate)
@@ -142,6 +162,7 @@ void Exchange::run_all(Ctx &ctx) const {   // x, then y, then z (edges/corners p
   for (int d = 0; d < 3; ++d) {
     launch_copy_ops(ctx, local[d]);
     if (key0 >= 0) ctx.comm.handshake(ctx, CH_ARRIVED, mask[d]);
+    launch_copy_ops(ctx, unpack[d]);
   }
 }
 

@@ -175,6 +175,7 @@ struct NbTable {   // neighbour box ids (global, -1: none) of one local box in t
 };
 struct Exchange {
   DevOps<CopyOp> local[3];
+  DevOps<CopyOp> unpack[3];        // after the neighbours' pushes have arrived: landing buffers -> ghost planes (x-faces)
   unsigned mask[3] = {0, 0, 0};   // peer processes this exchange pushes to / receives from, per direction
   int key0 = -1;                  // arena key of the first exchanged array (remote neighbours), -1: local only
   // nbs == nullptr: the boxes' physical neighbour tables
@@ -417,7 +418,8 @@ constexpr int MAXPROC = 16;
 enum CommChannel : int { CH_READY = 0, CH_ARRIVED = 1, CH_FFT = 2, CH_SOLVED = 3, CH_REDUCE = 4, CH_COUNT = 5 };
 enum ArenaKey : int {   // exported arrays: per box (rank) or per block
   AK_U0 = 0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P, AK_PP, AK_S0 /* .. AK_S0+7 */, AK_SLAB_X = 24, AK_SLAB_B = 25,
-  AK_SLAB_X1 = 26, AK_SLAB_K1 = 27, AK_SLAB_K2 = 28   // the other arrays that can hold the solver's level-0 iterate (MGSolver::xslot)
+  AK_SLAB_X1 = 26, AK_SLAB_K1 = 27, AK_SLAB_K2 = 28,  // the other arrays that can hold the solver's level-0 iterate (MGSolver::xslot)
+  AK_XSTAGE = 64   // + 2 * (key of the field) + side: dense landing buffer of an x-face pushed by the neighbour (bound.cu)
 };
 struct ArenaRec { int id, key; long long off; };   // id: box rank or block; off: bytes from the arena base
 constexpr int MAXREC = 1024;
