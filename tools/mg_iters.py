@@ -1,4 +1,6 @@
-"""Diagnostic: V-cycles per wavenumber plane of the TGV benchmark case (run on a GPU box)."""
+"""Diagnostic: V-cycles per wavenumber plane of the TGV benchmark case (run on a GPU box).  With a library built
+with -DSNAC_COARSE_TIMING (tools/build_variant.py, SNAC_B200_LIB=...) the coarse kernel also prints the clock
+cycles of its phases for plane q = 1."""
 import os, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
