@@ -53,3 +53,31 @@ def test_geometry_and_grid_files_round_trip(tmp_path):
         assert np.array_equal(g.rf[1:-1], ref.rf[1:-1]) and np.array_equal(g.drc[1:-1], ref.drc[1:-1])
         raw = np.fromfile(os.path.join(out, f"grid_{c}_b_001.bin")).reshape((int(blk.ng[d]), 4), order="F")
         assert np.array_equal(raw[:, 1], ref.rc[1:-1])            # column 1 = cell centres (reference reader)
+
+
+def _write_box(args):
+    fn, ng, lo, hi, seed, first = args
+    import numpy as np
+    from snac_b200 import load
+    n = [hi[d] - lo[d] + 1 for d in range(3)]
+    p = np.zeros([x + 2 for x in n], order="F")
+    p[1:-1, 1:-1, 1:-1] = np.random.default_rng(seed).standard_normal(n)
+    load.load_one("w", fn, ng, lo, hi, p, time=0.5, istep=7, write_info=first)
+    return p[1:-1, 1:-1, 1:-1]
+
+
+def test_boxes_of_a_block_written_by_separate_processes(tmp_path):
+    """one process per GPU writes its boxes of the same block file (the MPI-IO sub-array views of the
+    reference, src/load.f90:161-187): disjoint regions through memory maps, any order."""
+    import multiprocessing as mp
+    ng = (8, 6, 4)
+    fn = str(tmp_path / "fld_b_001_p.bin")
+    boxes = [((1, 1, 1), (4, 3, 4), 11, True), ((5, 1, 1), (8, 3, 4), 12, False),
+             ((1, 4, 1), (4, 6, 4), 13, False), ((5, 4, 1), (8, 6, 4), 14, False)]
+    with mp.get_context("spawn").Pool(4) as pool:
+        parts = pool.map(_write_box, [(fn, ng, lo, hi, seed, first) for lo, hi, seed, first in boxes])
+    raw = np.fromfile(fn)
+    full = raw[:-2].reshape(ng, order="F")
+    for (lo, hi, _, _), part in zip(boxes, parts):
+        assert np.array_equal(full[lo[0] - 1:hi[0], lo[1] - 1:hi[1], lo[2] - 1:hi[2]], part)
+    assert raw[-2] == 0.5 and raw[-1] == 7.0
