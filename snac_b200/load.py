@@ -1,6 +1,7 @@
 """Field/checkpoint files in the reference's on-disk layout, written from and read into device fields.
 
-Twin of ``load_one``/``io_field`` (reference ``src/load.f90:84-187``) and of the ``geometry_b_###.out`` record (``src/main.f90:428-438``), so that
+Twin of ``load_one``/``io_field`` (reference ``src/load.f90:84-187``), of ``out3d``/``write_log_output``
+(``src/output.f90:227-303``) and of the ``geometry_b_###.out`` record (``src/main.f90:428-438``), so that
 a run of this library and a run of the reference can restart from each other's ``fld_b_###_{u,v,w,p}.bin``
 and the reference's post-processing readers (``utils/read_binary_data``) work unchanged.
 
@@ -21,6 +22,50 @@ from .initgrid import save_grid   # ``save_grid`` (src/initgrid.f90:128-143)
 
 def _expected_size(ng) -> int:
     return (int(np.prod(np.asarray(ng, dtype=np.int64))) + 2) * 8
+
+
+def out3d(fname: str, ng, lo, hi, p: np.ndarray, nh=(1, 1, 1)) -> None:
+    """``out3d`` (src/output.f90:227-257): the block-global interior array, Fortran order, FP64, no trailer;
+    each box writes its part (``io_field``, src/load.f90:161-187)."""
+    ng = [int(x) for x in ng]
+    n = [int(hi[d]) - int(lo[d]) + 1 for d in range(3)]
+    ntot = int(np.prod(np.asarray(ng, dtype=np.int64)))
+    if not os.path.exists(fname) or os.path.getsize(fname) != ntot * 8:
+        with open(fname, "wb") as f:
+            f.truncate(ntot * 8)
+    mm = np.memmap(fname, dtype=np.float64, mode="r+", shape=(ntot,))
+    mm.reshape(ng, order="F")[tuple(slice(int(lo[d]) - 1, int(hi[d])) for d in range(3))] = \
+        p[tuple(slice(nh[d], nh[d] + n[d]) for d in range(3))]
+    mm.flush()
+    del mm
+
+
+def write_log_output(fname: str, fname_fld: str, varname: str, nmin, nmax, nskip, time: float, istep: int) -> None:
+    """``write_log_output`` (src/output.f90:259-285): one line ``(A,A,A,9i5,E15.7,i10)`` per saved field, from
+    which the reference's ``utils/visualize_fields`` scripts generate the xdmf file."""
+    from .initgrid import _e15_7
+    ints = "".join(f"{int(v):5d}" for v in (*nmin, *nmax, *nskip))
+    with open(fname, "a") as f:
+        f.write(f"{fname_fld} {varname}{ints}{_e15_7(float(time))}{int(istep):10d}\n")
+
+
+def out3d_hook(sim, datadir: str, fldnum: str, ranks=None) -> None:
+    """The calls of ``out3d.h90`` (``write_visu_3d`` for u,v,w,p and the scalars, src/output.f90:287-303):
+    ``vex|vey|vez|pre_fld_<fldnum>_b_###.bin`` + a line each in ``log_visu_3d_b_###.out``."""
+    from . import lib as L
+    os.makedirs(datadir, exist_ok=True)
+    names = [("vex", "Velocity_X", L.FIELD_U), ("vey", "Velocity_Y", L.FIELD_V), ("vez", "Velocity_Z", L.FIELD_W),
+             ("pre", "Pressure_P", L.FIELD_P)]
+    names += [(f"sca_{i + 1:03d}", f"Scalar_S{i + 1:03d}", L.FIELD_S0 + i) for i in range(sim.case.params.nscal)]
+    for r in (sim.ranks if ranks is None else ranks):
+        ib, ng, lo1, hi1, first = _block_frame(sim.case, r)
+        cblock = f"{ib + 1:03d}"
+        for stem, varname, fid in names:
+            fname_bin = f"{stem}_fld_{fldnum}_b_{cblock}.bin"
+            out3d(os.path.join(datadir, fname_bin), ng, lo1, hi1, sim.download(r, fid))
+            if first:   # myid_block == 0
+                write_log_output(os.path.join(datadir, f"log_visu_3d_b_{cblock}.out"), fname_bin, varname, (1, 1, 1),
+                                 tuple(int(x) for x in ng), (1, 1, 1), sim.time, sim.istep)
 
 
 def load_one(io: str, filename: str, ng, lo, hi, p: np.ndarray, nh=(1, 1, 1), time: float = 0.0, istep: int = 0,

@@ -81,3 +81,27 @@ def test_boxes_of_a_block_written_by_separate_processes(tmp_path):
     for (lo, hi, _, _), part in zip(boxes, parts):
         assert np.array_equal(full[lo[0] - 1:hi[0], lo[1] - 1:hi[1], lo[2] - 1:hi[2]], part)
     assert raw[-2] == 0.5 and raw[-1] == 7.0
+
+
+def test_out3d_and_visu_log_follow_the_reference_formats(tmp_path):
+    """out3d (src/output.f90:227-257) and write_log_output (:259-285): file = the block array alone; log line
+    '(A,A,A,9i5,E15.7,i10)' as parsed by the reference's utils/visualize_fields scripts (whitespace split)."""
+    ng = (5, 4, 3)
+    full = np.random.default_rng(9).standard_normal(ng)
+    fn = str(tmp_path / "vex_fld_0000100_b_001.bin")
+    for lo, hi in (((1, 1, 1), (5, 4, 1)), ((1, 1, 2), (5, 4, 3))):   # two boxes split in z
+        n = [hi[d] - lo[d] + 1 for d in range(3)]
+        p = np.zeros([x + 2 for x in n], order="F")
+        p[1:-1, 1:-1, 1:-1] = full[lo[0] - 1:hi[0], lo[1] - 1:hi[1], lo[2] - 1:hi[2]]
+        load.out3d(fn, ng, lo, hi, p)
+    assert os.path.getsize(fn) == np.prod(ng) * 8
+    assert np.array_equal(np.fromfile(fn).reshape(ng, order="F"), full)
+    log = str(tmp_path / "log_visu_3d_b_001.out")
+    load.write_log_output(log, "vex_fld_0000100_b_001.bin", "Velocity_X", (1, 1, 1), ng, (1, 1, 1), 12.5, 100)
+    load.write_log_output(log, "vey_fld_0000100_b_001.bin", "Velocity_Y", (1, 1, 1), ng, (1, 1, 1), 12.5, 100)
+    lines = open(log).read().splitlines()
+    assert len(lines) == 2
+    assert lines[0] == "vex_fld_0000100_b_001.bin Velocity_X" + "    1" * 3 + "    5    4    3" + "    1" * 3 + "  0.1250000E+02       100"
+    tok = lines[1].split()
+    assert tok[0] == "vey_fld_0000100_b_001.bin" and tok[1] == "Velocity_Y" and [int(t) for t in tok[2:11]] == [1, 1, 1, 5, 4, 3, 1, 1, 1]
+    assert float(tok[11]) == 12.5 and int(tok[12]) == 100
