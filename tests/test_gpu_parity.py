@@ -378,6 +378,39 @@ def test_out1d_out2d_on_the_device(tmp_path, kind, fa):
     g.close()
 
 
+def test_driver_runs_a_case_directory_like_program_snac(tmp_path):
+    """snac_b200.main.run = the start-up and time loop of src/main.f90 on a run directory with dns.nml/blocks.nml:
+    the files of data/ (time.out, out1d profiles, out3d fields + visu log, checkpoint, geometry, grids) are there
+    in the reference's formats and hold the device fields; read the way tests/lid_driven_cavity/test.py does."""
+    from snac_b200 import main as drv
+    rundir = str(tmp_path / "run")
+    cases.make("duct", rundir, fft_axis=1)
+    txt = open(os.path.join(rundir, "dns.nml")).read()
+    txt = txt.replace("nstep = 10,", "nstep = 6,").replace("icheck = 10, iout0d = 10, iout1d = 0, iout2d = 0, iout3d = 0, isave = 0",
+                                                           "icheck = 3, iout0d = 2, iout1d = 3, iout2d = 0, iout3d = 6, isave = 6")
+    open(os.path.join(rundir, "dns.nml"), "w").write(txt)
+    import io
+    log = io.StringIO()
+    sim = drv.run(rundir, fft_axis=1, log=log)
+    data = os.path.join(rundir, "data")
+    assert sim.istep == 6 and "Timestep # 6" in log.getvalue() and "Maximum divergence" in log.getvalue()
+    t = np.loadtxt(os.path.join(data, "time.out"))
+    assert t.shape == (3, 3) and list(t[:, 0]) == [2.0, 4.0, 6.0] and abs(t[-1, 2] - sim.time) <= 6e-7 * sim.time
+    for ib in range(4):
+        cb = f"{ib + 1:03d}"
+        geo = np.loadtxt(os.path.join(data, f"geometry_b_{cb}.out"), max_rows=4)     # read_single_field_binary.py
+        ng = (geo[1] - geo[0] + 1).astype(int)
+        fld = np.fromfile(os.path.join(data, f"vey_fld_0000006_b_{cb}.bin")).reshape(tuple(ng), order="F")
+        r = [q for q, b in enumerate(sim.case.world.boxes) if b.block == ib][0]
+        assert np.array_equal(fld, sim.download(r, L.FIELD_V)[1:-1, 1:-1, 1:-1])
+        chk = np.fromfile(os.path.join(data, f"fld_b_{cb}_u.bin"))
+        assert chk.size == np.prod(ng) + 2 and chk[-1] == 6.0
+        assert os.path.exists(os.path.join(data, f"umean_z_fld_0000003_b_{cb}.out"))
+        assert os.path.exists(os.path.join(data, f"pmean_x_fld_0000006_b_{cb}.out"))
+        assert len(open(os.path.join(data, f"log_visu_3d_b_{cb}.out")).read().splitlines()) == 4
+    sim.close()
+
+
 def test_checkpoint_restart_in_the_reference_layout(tmp_path):
     """fld_b_###_{u,v,w,p}.bin written from the device fields (snac_b200/load.py; src/load.f90:84-187,
     src/main.f90:1090-1117), restart from them (src/main.f90:542-556): the restarted run continues like the
