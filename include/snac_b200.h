@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SNAC_ABI_VERSION 1
+#define SNAC_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SNAC_API __attribute__((visibility("default")))
@@ -84,6 +84,10 @@ typedef struct snac_params {
   /* multigrid tuning (0 = default) */
   int mg_npre, mg_npost, mg_nbottom;
   int mg_generic;         /* 1: always use the general multi-box multigrid kernels */
+  /* solver of the per-wavenumber 2-D problems (fft_axis > 0): 0 = auto (the direct solver where every plane is one
+   * rectangle with a uniform periodic/Neumann/Dirichlet direction, multigrid otherwise), 1 = multigrid, 2 = direct
+   * (snac_commit fails where the planes are not separable) */
+  int plane_solver;
 } snac_params;
 
 /* Per-box description: the outputs of initmpi / initgrid / read_input that the hot path uses
@@ -172,6 +176,8 @@ SNAC_API int snac_solver_stats(snac_handle *h, int *iters, double *relres);
 /* V-cycles of the most recent solve averaged over the independent 2-D problems (wavenumbers): each
  * one stops on its own residual, as the reference's one-solve-per-wavenumber loop does */
 SNAC_API int snac_solver_mean_iters(snac_handle *h, double *mean_iters);
+/* which solver handles the pressure problem: 1 = multigrid, 2 = direct (transform + tridiagonal) */
+SNAC_API int snac_plane_solver(const snac_handle *h);
 /* Per-kernel-class device timing.  While enabled, every class section is bracketed by CUDA events
  * on the handle's stream and waited for, so the stream is serialised: use it to attribute time, not
  * to measure throughput.  Classes are numbered from 0; snac_profile_name returns NULL past the end. */

@@ -38,7 +38,9 @@ def _load():
     if _lib is None:
         L = C.CDLL(build())
         L.snac_cpu_create.restype = C.c_void_p
-        L.snac_cpu_create.argtypes = [C.c_int] * 3 + [C.c_double] * 5 + [C.c_int]
+        L.snac_cpu_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_double, C.c_int]
+        L.snac_cpu_init_bc.argtypes = [C.c_void_p]
+        L.snac_cpu_set_threads.argtypes = [C.c_int]
         L.snac_cpu_destroy.argtypes = [C.c_void_p]
         L.snac_cpu_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.snac_cpu_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -54,14 +56,32 @@ def _load():
     return _lib
 
 
-class CpuSim:
-    """One triperiodic block, uniform grid, FFT along z."""
+def use_all_cores():
+    """All host cores for the OpenMP loops, whatever OMP_NUM_THREADS says (torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would turn the baseline into a single-thread run)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    _load().snac_cpu_set_threads(int(n))
+    return int(n)
 
-    def __init__(self, n, lengths, visc, tol=1e-4, maxiter=50):
+
+class CpuSim:
+    """One rectangular domain on a uniform grid; ``walls[d]``: no-slip walls (else periodic) in
+    direction d; transforms along ``fft_axis`` (1, 2 or 3: a periodic direction)."""
+
+    def __init__(self, n, lengths, visc, tol=1e-4, maxiter=50, walls=(0, 0, 0), fft_axis=3, bforce=(0.0, 0.0, 0.0)):
         self.L = _load()
         self.n = tuple(int(x) for x in n)
-        self.h = self.L.snac_cpu_create(*self.n, *[float(x) for x in lengths], float(visc), float(tol), int(maxiter))
+        ni = (C.c_int * 3)(*self.n)
+        le = (C.c_double * 3)(*[float(x) for x in lengths])
+        wa = (C.c_int * 3)(*[int(bool(x)) for x in walls])
+        bf = (C.c_double * 3)(*[float(x) for x in bforce])
+        self.h = self.L.snac_cpu_create(ni, le, wa, int(fft_axis), float(visc), bf, float(tol), int(maxiter))
+        if not self.h:
+            raise ValueError("snac_cpu_create: the transform axis must be a periodic direction (or out of memory)")
         self.shape = tuple(x + 2 for x in self.n)
+
+    def init_bc(self):
+        self.L.snac_cpu_init_bc(self.h)
 
     @property
     def threads(self):

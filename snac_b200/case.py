@@ -35,35 +35,39 @@ def setup_case(rundir: str = ".", fft_axis: int = 0, impdiff: bool = False, bous
     return Case(params=p, world=world, bgrids=bg, grids=g, rundir=rundir)
 
 
-def initial_fields(case: Case, ranks=None, noise: bool = False):
+def initial_fields(case: Case, ranks=None, noise: bool = False, mean_reduce=None):
     """Initial u,v,w,p (+scalars) for the given ranks (default: all), ghosted Fortran-order arrays.
 
-    ``set_mean`` (reference src/initflow.f90:288-316) needs a sum over the boxes of a block, so the
-    local means of *all* boxes of the block are evaluated here even when only some ranks are
-    requested (cheap: one pass)."""
+    ``set_mean`` (reference src/initflow.f90:288-316) needs a sum over the boxes of a block
+    (MPI_ALLREDUCE over comm_block there).  ``mean_reduce`` = None: the local means of *all* boxes of
+    the block are evaluated here even when only some ranks are requested (one pass; fine for tests).
+    Several processes at benchmark sizes pass ``mean_reduce``: a callable that sums an array of
+    per-block partial means over the processes; each process then generates its own boxes only."""
     p, world = case.params, case.world
     ranks = list(range(world.nrank)) if ranks is None else list(ranks)
     out = {}
     need_blocks = {world.boxes[r].block for r in ranks}
     fields = {}
     for box in world.boxes:
-        if box.block not in need_blocks:
+        if box.block not in need_blocks or (mean_reduce is not None and box.rank not in ranks):
             continue
         b = p.blocks[box.block]
         l = b.lmax - b.lmin
         g = case.grids[box.rank]
         fields[box.rank] = _if.initflow(b.inivel, False, box, g, l, b.bcvel, p.visc, p.bforce[0],
                                         add_noise_to=noise)
-    for ib in need_blocks:
-        members = [bx.rank for bx in world.boxes if bx.block == ib]
-        b = p.blocks[ib]
-        l = b.lmax - b.lmin
-        if fields[members[0]][4]:  # is_mean
-            meanold = sum(_if.set_mean_local(case.grids[r].dxc, case.grids[r].dyf, case.grids[r].dzf, l,
-                                             fields[r][0]) for r in members)
-            if meanold != 0.0:
-                for r in members:
-                    fields[r][0][...] = fields[r][0] / meanold * fields[r][5]
+    part = np.zeros(len(p.blocks))
+    for r, f in fields.items():
+        if f[4]:  # is_mean
+            b = p.blocks[world.boxes[r].block]
+            part[world.boxes[r].block] += _if.set_mean_local(case.grids[r].dxc, case.grids[r].dyf, case.grids[r].dzf,
+                                                             b.lmax - b.lmin, f[0])
+    if mean_reduce is not None:
+        part = np.asarray(mean_reduce(part), dtype=np.float64)
+    for r, f in fields.items():
+        meanold = part[world.boxes[r].block]
+        if f[4] and meanold != 0.0:
+            f[0][...] = f[0] / meanold * f[5]
     for r in ranks:
         box = world.boxes[r]
         b = p.blocks[box.block]

@@ -723,6 +723,13 @@ static void do_solve(Ctx &ctx) {
   if (ctx.prm.fft_axis > 0) ctx.comm.handshake(ctx, CH_SOLVED, ~0u);
 }
 
+// after a stream synchronisation: did a handshake give up on a peer (comm.cu)?
+static void check_peers(Ctx &ctx) {
+  const int e = ctx.comm.error_state();
+  if (e == 1) throw Error("a peer process reported an error and left the run (see its snac_last_error)");
+  if (e == 2) throw Error("a peer process did not arrive at a handshake within the time limit (dead or hung)");
+}
+
 __global__ void publish_kernel(const double *vals, double *const *slots, int n, int nproc) {
   const int p = threadIdx.x;
   if (p < nproc) for (int i = 0; i < n; ++i) slots[p][i] = vals[i];
@@ -755,6 +762,7 @@ static void do_chk(Ctx &ctx, bool want_dt, double *out3) {
   ctx.comm.handshake(ctx, CH_REDUCE, ~0u);
   SNAC_CUDA(cudaMemcpyAsync(ctx.h_red, ctx.comm.arena + base, 4 * MAXPROC * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+  check_peers(ctx);
   out3[0] = 0.0; out3[1] = 0.0; out3[2] = 0.0;
   for (int p = 0; p < np; ++p) {
     out3[0] = std::max(out3[0], ctx.h_red[4 * p + 0]);
@@ -878,6 +886,7 @@ using namespace snac;
     return 0;                                     \
   } catch (const std::exception &e) {             \
     (h)->ctx.err = e.what();                      \
+    (h)->ctx.comm.signal_abort();                 \
     return -1;                                    \
   }
 
@@ -1041,10 +1050,14 @@ int snac_chkdt(snac_handle *h, double *dt_cfl) {
     if (dti == 0.0) dti = 1.0;
     double dtmax = std::sqrt(3.0) / dti;
     if (!ctx.prm.impdiff) {  // src/chkdt.f90:51-55
+      // MPI_ALLREDUCE(MIN) over every rank (src/chkdt.f90:52-53): the grids of all boxes of the run were recorded by
+      // snac_add_box, so every process takes the minimum over all of them and arrives at the same dt
       double dlmin = 1e300;
-      for (auto &b : ctx.boxes)
-        for (int d = 0; d < 3; ++d)
-          for (double v : b->h_df[d]) dlmin = std::min(dlmin, v);
+      for (int r = 0; r < ctx.prm.nrank; ++r)
+        for (int d = 0; d < 3; ++d) {
+          const std::vector<double> &df = ctx.world_set[r] ? ctx.world_df[d][r] : std::vector<double>();
+          for (double v : df) dlmin = std::min(dlmin, v);
+        }
       double alpha_max = 0.0;
       for (int s = 0; s < ctx.prm.nscal; ++s) alpha_max = std::max(alpha_max, 1.0 / ctx.prm.alphai[s]);
       const double visc = std::max(ctx.prm.visc, alpha_max);
@@ -1142,8 +1155,14 @@ int snac_timer_stop(snac_handle *h, double *ms) {
 int snac_solver_mean_iters(snac_handle *h, double *mean_iters) {
   SNAC_TRY(h, h->ctx.psolver.stats(h->ctx, nullptr, nullptr, mean_iters))
 }
+int snac_plane_solver(const snac_handle *h) { return h ? (h->ctx.direct_on ? 2 : 1) : -1; }
 long long snac_launch_count(const snac_handle *h) { return h ? h->ctx.launches : -1; }
-int snac_sync(snac_handle *h) { SNAC_TRY(h, SNAC_CUDA(cudaStreamSynchronize(h->ctx.stream))) }
+int snac_sync(snac_handle *h) {
+  SNAC_TRY(h, {
+    SNAC_CUDA(cudaStreamSynchronize(h->ctx.stream));
+    check_peers(h->ctx);
+  })
+}
 void *snac_stream(snac_handle *h) { return h ? (void *)h->ctx.stream : nullptr; }
 
 }  // extern "C"

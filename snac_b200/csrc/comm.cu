@@ -65,6 +65,22 @@ double *PeerComm::remote(int proc, int id, int key) const {
   throw Error("array (" + std::to_string(id) + "," + std::to_string(key) + ") is not published by process " + std::to_string(proc));
 }
 
+// error path: tell every peer to stop waiting for this process
+void PeerComm::signal_abort() {
+  if (!connected) return;
+  const long long one = 1;
+  for (int p = 0; p < nproc; ++p)
+    if (p != me && peer[p]) cudaMemcpy(peer[p] + ABORT_OFFSET, &one, sizeof(one), cudaMemcpyHostToDevice);
+}
+
+// 0: fine; 1: a peer aborted; 2: a peer never arrived (timeout).  Call after a stream synchronisation.
+int PeerComm::error_state() const {
+  if (!connected) return 0;
+  long long w[2] = {0, 0};
+  if (cudaMemcpy(w, arena + ABORT_OFFSET, sizeof(w), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  return (int)w[1];
+}
+
 void PeerComm::release() {
   for (int p = 0; p < nproc; ++p)
     if (p != me && peer[p]) cudaIpcCloseMemHandle(peer[p]);
@@ -75,16 +91,36 @@ void PeerComm::release() {
 struct HandshakeArgs {
   long long *remote_flag[MAXPROC];   // my slot in each peer's flag table (channel row already applied)
   volatile long long *local_flag;    // my own table row: local_flag[src]
+  volatile long long *abort_word;    // my arena: [0] set by a failing peer, [1] error raised here (read by the host)
   unsigned mask;
   long long seq;
 };
 
+__device__ inline unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// A peer that throws (any error path of the C ABI) sets the abort word of every arena; a peer that dies
+// never arrives: the wait is bounded (HANDSHAKE_TIMEOUT_S, far beyond any legitimate skew between the
+// processes).  Either way the kernel leaves the loop and raises the error word, which the host reads at
+// its next synchronisation point (snac_sync, chkdt/chkdiv) -- instead of hanging inside a kernel forever.
+constexpr unsigned long long HANDSHAKE_TIMEOUT_S = 900;
 __global__ void handshake_kernel(const HandshakeArgs a) {
   const int t = threadIdx.x;
   if (t >= MAXPROC || !((a.mask >> t) & 1u)) return;
   __threadfence_system();                       // everything this GPU wrote before is visible first
   *reinterpret_cast<volatile long long *>(a.remote_flag[t]) = a.seq;
-  while (a.local_flag[t] < a.seq) __nanosleep(64);
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
+  while (a.local_flag[t] < a.seq) {
+    __nanosleep(64);
+    if ((++spins & 1023u) == 0) {
+      if (a.abort_word[0] != 0) { a.abort_word[1] = 1; break; }
+      if (global_ns() - t0 > HANDSHAKE_TIMEOUT_S * 1000000000ull) { a.abort_word[1] = 2; break; }
+    }
+  }
   __threadfence_system();
 }
 
@@ -101,6 +137,7 @@ void PeerComm::handshake(Ctx &ctx, int ch, unsigned mask) {
       a.remote_flag[p] = reinterpret_cast<long long *>(peer[p]) + (size_t)ch * MAXPROC + me;
   }
   a.local_flag = reinterpret_cast<volatile long long *>(arena) + (size_t)ch * MAXPROC;
+  a.abort_word = reinterpret_cast<volatile long long *>(arena + ABORT_OFFSET);
   a.mask = mask;
   a.seq = seq[ch];
   handshake_kernel<<<1, 32, 0, ctx.stream>>>(a);

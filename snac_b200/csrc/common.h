@@ -333,13 +333,10 @@ struct MGSolver {
   int nq = 1;                      // number of independent planes (wavenumbers)
   DevBuf norms;                    // [2*nq]: sum r^2, sum b^2 per plane
   std::vector<double> h_norms;
-  bool use_tiles = false;
-  int plane_kernel = 0;            // 0: prefetch-ring kernels (mg_ring.cu), 1: shared-memory tiles, 2: register marching
   bool ids_local = false;          // neighbour ids of the solver boxes are solver-box indices (batched: blocks)
   bool plane_local = false;        // fused shared-memory path (planes not split over boxes)
   int first_smem_level = 0;        // first level handled by the one-CTA-per-plane kernel
   bool coarse_single = false;      // that kernel computes in FP32 (only ever a coarse-grid correction, never level 0)
-  bool coarse_old = false;         // A/B switch: the previous shared-memory kernel
   std::vector<Field3> x1;          // second x buffer of the tiled levels [level*nbox + box]
   int *d_active = nullptr, *d_where = nullptr, *d_iters = nullptr, *d_count = nullptr;  // per-plane stopping flags
   int *h_count = nullptr;          // pinned: [0] the polled counter, then the histories below
@@ -440,6 +437,12 @@ struct PeerComm {
   // layout of the head of every arena: flags[CH_COUNT][MAXPROC] (long long), then red[MAXPROC][4] (double)
   static constexpr size_t FLAGS_BYTES = CH_COUNT * MAXPROC * sizeof(long long);
   static constexpr size_t HEAD_BYTES = 4096;
+  // after the flags and the two reduction tables: [0] abort request written by a failing peer, [1] error raised by
+  // this process' handshake kernel (comm.cu)
+  static constexpr size_t ABORT_OFFSET = FLAGS_BYTES + 2 * MAXPROC * 4 * sizeof(double);
+  static_assert(ABORT_OFFSET + 16 <= HEAD_BYTES, "arena head layout");
+  void signal_abort();
+  int error_state() const;
   void init(int nproc_, int me_, size_t bytes);
   double *alloc(size_t elems, int id, int key);   // zero-initialised, 256-byte aligned, recorded for export
   void export_blob(CommBlob &b) const;
@@ -496,6 +499,7 @@ struct Ctx {
   // transforms and solvers
   R2RPlan plan_p;
   MGSolver psolver;
+  bool direct_on = false;                           // the direct plane solver handles the pressure problem
   std::unique_ptr<MGSolver> usolver[3][2];          // IMPDIFF: [component][velocity buffer]
   std::unique_ptr<MGSolver> ssolver[SNAC_MAX_SCAL];
   double fs[SNAC_MAX_SCAL] = {0};                   // accumulated scalar forcing (src/main.f90:913)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # SNAC_B200_LIB: an alternative build of the same library (kernel-tuning experiments, tools/build_variant.py)
 LIB_PATH = os.environ.get("SNAC_B200_LIB") or os.path.join(HERE, "libsnacb200.so")
 
-SNAC_ABI_VERSION = 1
+SNAC_ABI_VERSION = 2
 SNAC_MAX_SCAL = 8
 
 FIELD_U, FIELD_V, FIELD_W, FIELD_P, FIELD_PP, FIELD_RHS, FIELD_PO = range(7)
@@ -37,6 +37,7 @@ class snac_params(C.Structure):
         ("is_sforced", C.c_int * SNAC_MAX_SCAL), ("scalf", C.c_double * SNAC_MAX_SCAL),
         ("hypre_tol", C.c_double), ("hypre_maxiter", C.c_int), ("hypre_solver_i", C.c_int),
         ("mg_npre", C.c_int), ("mg_npost", C.c_int), ("mg_nbottom", C.c_int), ("mg_generic", C.c_int),
+        ("plane_solver", C.c_int),
     ]
 
 
@@ -85,6 +86,7 @@ EXPORTS = {
     "snac_step": (C.c_int, [C.c_void_p, C.c_double]),
     "snac_solver_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "snac_solver_mean_iters": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "snac_plane_solver": (C.c_int, [C.c_void_p]),
     "snac_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "snac_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "snac_profile_units": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),

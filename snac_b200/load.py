@@ -24,15 +24,27 @@ def _expected_size(ng) -> int:
     return (int(np.prod(np.asarray(ng, dtype=np.int64))) + 2) * 8
 
 
+def _ensure_file(fname: str, size: int) -> None:
+    """Creates the file if it is missing and gives it its size WITHOUT ever truncating existing contents: several
+    processes (one per GPU) call this for the same file of a block and then write their own sub-arrays.  ``open('wb')``
+    (O_TRUNC) here would wipe what a faster process has already written, or shrink the file under its live memory
+    map; O_CREAT without O_TRUNC plus ftruncate to the one size every process agrees on is idempotent (the reference
+    opens the file collectively and calls MPI_FILE_SET_SIZE, src/load.f90:141-143)."""
+    fd = os.open(fname, os.O_RDWR | os.O_CREAT, 0o644)
+    try:
+        if os.fstat(fd).st_size != size:
+            os.ftruncate(fd, size)
+    finally:
+        os.close(fd)
+
+
 def out3d(fname: str, ng, lo, hi, p: np.ndarray, nh=(1, 1, 1)) -> None:
     """``out3d`` (src/output.f90:227-257): the block-global interior array, Fortran order, FP64, no trailer;
     each box writes its part (``io_field``, src/load.f90:161-187)."""
     ng = [int(x) for x in ng]
     n = [int(hi[d]) - int(lo[d]) + 1 for d in range(3)]
     ntot = int(np.prod(np.asarray(ng, dtype=np.int64)))
-    if not os.path.exists(fname) or os.path.getsize(fname) != ntot * 8:
-        with open(fname, "wb") as f:
-            f.truncate(ntot * 8)
+    _ensure_file(fname, ntot * 8)
     mm = np.memmap(fname, dtype=np.float64, mode="r+", shape=(ntot,))
     mm.reshape(ng, order="F")[tuple(slice(int(lo[d]) - 1, int(hi[d])) for d in range(3))] = \
         p[tuple(slice(nh[d], nh[d] + n[d]) for d in range(3))]
@@ -91,9 +103,7 @@ def load_one(io: str, filename: str, ng, lo, hi, p: np.ndarray, nh=(1, 1, 1), ti
         del mm
         return info
     if io == "w":
-        if not os.path.exists(filename) or os.path.getsize(filename) != _expected_size(ng):
-            with open(filename, "wb") as f:
-                f.truncate(_expected_size(ng))
+        _ensure_file(filename, _expected_size(ng))
         mm = np.memmap(filename, dtype=np.float64, mode="r+", shape=(ntot + 2,))
         mm[:ntot].reshape(ng, order="F")[box] = p[inner]
         if write_info:

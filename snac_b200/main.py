@@ -20,10 +20,10 @@ import time as _time
 
 from . import load, output
 from .case import inflow_planes, initial_fields, setup_case
+from .dist import allreduce, barrier
 from .initgrid import _e15_7
+from .param import SMALL   # epsilon*10**(precision/2), src/param.f90:9
 from .sim import Simulation
-
-SMALL = 1.0e-9   # src/param.f90
 
 
 def out0d(fname, var):
@@ -52,6 +52,9 @@ def run(rundir, fft_axis=0, impdiff=False, boussinesq=False, device=0, nproc=1, 
     if any(f.any() for f in flags.values()):
         sim.set_inflow(planes)
     sim.init_bc()
+    fldnum = f"{sim.istep:07d}"                                  # post-process and write the initial condition
+    output.out1d_hook(sim, datadir, fldnum)                     # src/main.f90:654-656
+    load.out3d_hook(sim, datadir, fldnum)
     sim.set_dt()                                                # src/main.f90:660-662
     if root:
         print(f"dt_cfl = {sim.dt_cfl} dt = {sim.dt}", file=log)
@@ -67,8 +70,10 @@ def run(rundir, fft_axis=0, impdiff=False, boussinesq=False, device=0, nproc=1, 
             is_done = True
         if P.stop_type[1] and sim.time >= P.time_max:
             is_done = True
-        if P.stop_type[2] and (_time.time() - twi) / 3600.0 >= P.tw_max:
-            is_done = True
+        if P.stop_type[2]:   # the slowest process decides (MPI_ALLREDUCE(MAX) of tw, src/main.f90:1043-1046):
+            tw = float(allreduce([(_time.time() - twi) / 3600.0], "max")[0])   # all processes leave the loop together
+            if tw >= P.tw_max:
+                is_done = True
         if P.icheck > 0 and sim.istep % P.icheck == 0:
             sim.set_dt()
             if root:
@@ -87,6 +92,8 @@ def run(rundir, fft_axis=0, impdiff=False, boussinesq=False, device=0, nproc=1, 
             out0d(os.path.join(datadir, "time.out"), (1.0 * sim.istep, sim.dt, sim.time))
         if P.iout1d > 0 and sim.istep % P.iout1d == 0:
             output.out1d_hook(sim, datadir, fldnum)
+        if P.iout2d > 0 and sim.istep % P.iout2d == 0:
+            output.out2d_hook(sim, datadir, fldnum)
         if P.iout3d > 0 and sim.istep % P.iout3d == 0:
             load.out3d_hook(sim, datadir, fldnum)
         if P.isave > 0 and (sim.istep % P.isave == 0 or (is_done and not kill)):
@@ -101,6 +108,7 @@ def run(rundir, fft_axis=0, impdiff=False, boussinesq=False, device=0, nproc=1, 
                     if root:
                         out0d(os.path.join(datadir, "log_saves.out"), (1.0 * sim.istep, sim.time, 1.0 * ichkpt))
             load.write_checkpoint(sim, datadir, basename=base)
+            barrier()                                           # every box of a file is on disk before anything reads or links it
             if not P.is_overwrite_save and root:                # fld_* -> last checkpoint (symbolic links)
                 for ib in range(len(P.blocks)):
                     for suffix in ["u", "v", "w", "p"] + [f"s_{i + 1:03d}" for i in range(P.nscal)]:

@@ -10,6 +10,7 @@ import os
 import numpy as np
 
 from . import lib as L
+from .dist import allreduce
 from .initgrid import _e15_7
 
 
@@ -41,7 +42,7 @@ def block_profile(sim, block, field, idir, stag=-1):
         sim._chk(sim.lib.snac_out1d(sim.h, box.rank, field, idir, _ptr(w[a]), _ptr(w[b_]), 1.0 / (l[a] * l[b_]), _ptr(p1d)))
         s = int(box.lo[idir] - lo_g[idir])
         out[s:s + p1d.size] += p1d
-    return out
+    return allreduce(out)   # MPI_ALLREDUCE over comm_block (src/output.f90:79-86): boxes of other processes
 
 
 def block_average(sim, block, field, idir, stag=-1):
@@ -61,17 +62,25 @@ def block_average(sim, block, field, idir, stag=-1):
         sim._chk(sim.lib.snac_out2d(sim.h, box.rank, field, idir, _ptr(w[idir]), 1.0 / l[idir], _ptr(p2d)))
         sa, sb = int(box.lo[a] - lo_g[a]), int(box.lo[b_] - lo_g[b_])
         out[sa:sa + p2d.shape[0], sb:sb + p2d.shape[1]] += p2d
-    return out
+    return np.asfortranarray(allreduce(np.ascontiguousarray(out)))   # src/output.f90:170-177
+
+
+def _is_block_root(sim, block):
+    """myid_block == 0: the process owning the first box of the block writes its files (src/output.f90:87)."""
+    first = min(b.rank for b in sim.case.world.boxes if b.block == block)
+    return first in sim.ranks
 
 
 def out1d(fname, sim, block, field, idir, stag=-1):
-    """``out1d`` (src/output.f90:34-133): two columns ``(2E15.7)``: coordinate, profile."""
+    """``out1d`` (src/output.f90:34-133): two columns ``(2E15.7)``: coordinate, profile.  Collective over the
+    processes (every one calls it); the block's first process writes the file."""
     p1d = block_profile(sim, block, field, idir, stag)
     g = sim.case.bgrids[block][idir]
     coord = (g.rf if idir == stag else g.rc)[1:-1]
-    with open(fname, "w") as f:
-        for x, v in zip(coord, p1d):
-            f.write(_e15_7(float(x)) + _e15_7(float(v)) + "\n")
+    if _is_block_root(sim, block):
+        with open(fname, "w") as f:
+            for x, v in zip(coord, p1d):
+                f.write(_e15_7(float(x)) + _e15_7(float(v)) + "\n")
     return p1d
 
 
@@ -82,10 +91,11 @@ def out2d(fname, sim, block, field, idir, stag=-1):
     ga, gb = sim.case.bgrids[block][a], sim.case.bgrids[block][b_]
     ca = (ga.rf if a == stag else ga.rc)[1:-1]
     cb = (gb.rf if b_ == stag else gb.rc)[1:-1]
-    with open(fname, "w") as f:
-        for jb in range(p2d.shape[1]):
-            for ia in range(p2d.shape[0]):
-                f.write(_e15_7(float(ca[ia])) + _e15_7(float(cb[jb])) + _e15_7(float(p2d[ia, jb])) + "\n")
+    if _is_block_root(sim, block):
+        with open(fname, "w") as f:
+            for jb in range(p2d.shape[1]):
+                for ia in range(p2d.shape[0]):
+                    f.write(_e15_7(float(ca[ia])) + _e15_7(float(cb[jb])) + _e15_7(float(p2d[ia, jb])) + "\n")
     return p2d
 
 
@@ -98,3 +108,16 @@ def out1d_hook(sim, datadir, fldnum):
         for name, field, stag in (("u", L.FIELD_U, 0), ("v", L.FIELD_V, 1), ("w", L.FIELD_W, 2), ("p", L.FIELD_P, -1)):
             for idir, c in enumerate("xyz"):
                 out1d(os.path.join(datadir, f"{name}mean_{c}_fld_{fldnum}_b_{cblock}.out"), sim, ib, field, idir, stag)
+
+
+def out2d_hook(sim, datadir, fldnum, enabled=False):
+    """The calls of ``out2d.h90``.  The reference ships that include file with every call commented out
+    (src/out2d.h90:14-25), so on the ``iout2d`` cadence it writes nothing; the same here unless ``enabled``, which
+    writes the four z-averaged planes the commented calls name (``{u,v,w,p}mean_2d_z_fld_<fldnum>_b_###.out``)."""
+    if not enabled:
+        return
+    os.makedirs(datadir, exist_ok=True)
+    for ib in range(len(sim.case.params.blocks)):
+        cblock = f"{ib + 1:03d}"
+        for name, field, stag in (("u", L.FIELD_U, 0), ("v", L.FIELD_V, 1), ("w", L.FIELD_W, 2), ("p", L.FIELD_P, -1)):
+            out2d(os.path.join(datadir, f"{name}mean_2d_z_fld_{fldnum}_b_{cblock}.out"), sim, ib, field, 2, stag)

@@ -28,7 +28,8 @@ class Simulation:
     def __init__(self, case: Case, ranks: Optional[Iterable[int]] = None, device: int = 0,
                  nproc: int = 1, myproc: int = 0, rank_owner: Optional[List[int]] = None,
                  tol: Optional[float] = None, maxiter: Optional[int] = None,
-                 mg_npre: int = 0, mg_npost: int = 0, mg_nbottom: int = 0, mg_generic: bool = False):
+                 mg_npre: int = 0, mg_npost: int = 0, mg_nbottom: int = 0, mg_generic: bool = False,
+                 solver: str = "auto"):
         self.case = case
         P, W = case.params, case.world
         self.lib = L.load_library()
@@ -57,6 +58,7 @@ class Simulation:
         prm.hypre_solver_i = int(P.hypre_solver_i)
         prm.mg_npre, prm.mg_npost, prm.mg_nbottom = mg_npre, mg_npost, mg_nbottom
         prm.mg_generic = int(mg_generic)
+        prm.plane_solver = {"auto": 0, "mg": 1, "direct": 2}[solver]
         h = C.c_void_p()
         if self.lib.snac_create(C.byref(prm), C.byref(h)) != 0:
             raise L.SnacError(self.lib.snac_last_error(None).decode())
@@ -206,6 +208,9 @@ class Simulation:
         v = C.c_double()
         self._chk(self.lib.snac_solver_mean_iters(self.h, C.byref(v)))
         return v.value
+
+    def solver_name(self):
+        return {1: "mg", 2: "direct"}[int(self.lib.snac_plane_solver(self.h))]
 
     def launch_count(self):
         return int(self.lib.snac_launch_count(self.h))

@@ -32,17 +32,75 @@ def test_blob_gather_is_ordered_by_process():
     assert res[0] == expect and res[1] == expect
 
 
-def test_weak_scaling_decomposition_matches_gpu_count(tmp_path):
-    """bench.py's N-GPU workload: one box per GPU, transform axis whole, 256^3 cells per box."""
+def test_bench_decompositions_match_gpu_count(tmp_path):
+    """bench.py's N-GPU workloads: one box per GPU with the transform axis whole -- the channel strong-scaled
+    over block_dims (1,1,1)/(2,1,1)/(2,1,2)/(4,1,2), the TGV weak-scaled, the duct as 4 or 8 friend blocks."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
     import bench
-    for n, dims in bench.DIMS.items():
-        case = bench.make_tgv(16, dims, str(tmp_path / f"n{n}"))
-        assert case.world.nrank == n
-        assert dims[2] == 1                              # z (FFT_AXIS=3) is never split
+    for n in (1, 2, 4, 8):
+        case, owner, scaling, topo = bench.make_case("channel", (32, 16, 16), n, str(tmp_path / f"c{n}"))
+        assert case.world.nrank == n and sorted(owner) == list(range(n)) and scaling == "strong"
+        assert all(int(b.n[1]) == 16 for b in case.world.boxes)          # y (FFT_AXIS=2) is never split
+        assert sum(int(np.prod(b.n)) for b in case.world.boxes) == 32 * 16 * 16
+        assert topo == ((0, 0, 1), 2) and tuple(case.world.periods) == (32, 16, 0)
+        case, owner, scaling, topo = bench.make_case("tgv", (16, 16, 16), n, str(tmp_path / f"t{n}"))
+        assert case.world.nrank == n and scaling == "weak"
         assert all(tuple(b.n) == (16, 16, 16) for b in case.world.boxes)
-        assert np.all(case.world.periods == np.array(dims) * 16)
+        assert np.all(case.world.periods == np.array(bench.TGV_DIMS[n]) * 16)
+        case, owner, scaling, topo = bench.make_case("duct", (16, 16, 16), n, str(tmp_path / f"d{n}"))
+        assert case.world.nrank == (8 if n == 8 else 4) and len(case.params.blocks) == case.world.nrank
+        assert set(owner) == set(range(n)) and all(int(b.n[0]) == 16 for b in case.world.boxes)
+        assert tuple(case.world.periods) == (16, 0, 0)
+
+
+def _out1d_worker(rank, world, port, rundir, datadir, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    sys.path.insert(0, os.path.dirname(__file__))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from test_output_host import _Sim
+    from snac_b200 import output
+    from snac_b200.case import setup_case
+    case = setup_case(rundir, fft_axis=2)
+    sim = _Sim(case)                                                    # same seeded fields in every process
+    sim.ranks = [r for r in range(case.world.nrank) if r % world == rank]   # ... of which it owns these boxes
+    p1d = output.out1d(os.path.join(datadir, "wmean_z.out"), sim, 0, 2, 2, stag=2)
+    p2d = output.block_average(sim, 0, 3, 1)
+    q.put((rank, p1d, p2d, os.path.exists(os.path.join(datadir, "wmean_z.out"))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_out1d_out2d_reduce_over_the_processes_of_a_block(tmp_path):
+    """out1d/out2d with the boxes of a block dealt to two processes (MPI_ALLREDUCE over comm_block,
+    src/output.f90:79-86,170-177): both get the whole-block profile, the block's first process writes the file."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import cases
+    from test_output_host import _Sim
+    from snac_b200 import output
+    rundir, datadir = str(tmp_path / "run"), str(tmp_path / "data")
+    os.makedirs(datadir)
+    case = cases.make("channel", rundir, fft_axis=2)
+    ref1 = output.block_profile(_Sim(case), 0, 2, 2, 2)
+    ref2 = output.block_average(_Sim(case), 0, 3, 1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 300
+    ps = [ctx.Process(target=_out1d_worker, args=(r, 2, port, rundir, datadir, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, p1d, p2d, _ in res:
+        assert np.allclose(p1d, ref1, rtol=1e-13, atol=1e-15) and np.allclose(p2d, ref2, rtol=1e-13, atol=1e-15)
+    tab = np.loadtxt(os.path.join(datadir, "wmean_z.out"))
+    assert np.allclose(tab[:, 1], ref1, rtol=6e-7, atol=1e-9)
 
 
 class _FakeSim:

@@ -105,3 +105,65 @@ def test_out3d_and_visu_log_follow_the_reference_formats(tmp_path):
     tok = lines[1].split()
     assert tok[0] == "vey_fld_0000100_b_001.bin" and tok[1] == "Velocity_Y" and [int(t) for t in tok[2:11]] == [1, 1, 1, 5, 4, 3, 1, 1, 1]
     assert float(tok[11]) == 12.5 and int(tok[12]) == 100
+
+
+def test_a_late_creator_does_not_wipe_boxes_already_written(tmp_path, monkeypatch):
+    """The interleaving behind the checkpoint race: process B decided the file was missing, process A then
+    created it and wrote its box, and only now B gets to create it.  With open('wb') (O_TRUNC) B wiped A's box;
+    creation must never truncate."""
+    ng = (4, 4, 2)
+    fn = str(tmp_path / "fld_b_001_v.bin")
+    a = np.zeros((6, 4, 4), order="F"); a[1:-1, 1:-1, 1:-1] = 1.5
+    b = np.zeros((6, 4, 4), order="F"); b[1:-1, 1:-1, 1:-1] = 2.5
+    load.load_one("w", fn, ng, (1, 1, 1), (4, 2, 2), a, time=3.0, istep=9, write_info=True)
+    # B's stale view of the directory: it still believes the file does not exist
+    monkeypatch.setattr(os.path, "exists", lambda p: False)
+    load.load_one("w", fn, ng, (1, 3, 1), (4, 4, 2), b, write_info=False)
+    monkeypatch.undo()
+    raw = np.fromfile(fn)
+    full = raw[:-2].reshape(ng, order="F")
+    assert np.all(full[:, :2, :] == 1.5) and np.all(full[:, 2:, :] == 2.5)
+    assert raw[-2] == 3.0 and raw[-1] == 9.0
+    # a stale file of another size (a previous run on another grid) is resized, not appended to
+    with open(fn, "ab") as f:
+        f.write(b"\0" * 64)
+    load.load_one("w", fn, ng, (1, 1, 1), (4, 2, 2), a, time=4.0, istep=10, write_info=True)
+    assert os.path.getsize(fn) == (np.prod(ng) + 2) * 8
+    # the same for out3d files
+    fo = str(tmp_path / "pre_fld_0000001_b_001.bin")
+    load.out3d(fo, ng, (1, 1, 1), (4, 2, 2), a)
+    monkeypatch.setattr(os.path, "exists", lambda p: False)
+    load.out3d(fo, ng, (1, 3, 1), (4, 4, 2), b)
+    monkeypatch.undo()
+    full = np.fromfile(fo).reshape(ng, order="F")
+    assert np.all(full[:, :2, :] == 1.5) and np.all(full[:, 2:, :] == 2.5)
+
+
+REF_READER = "/root/reference/utils/read_binary_data/python"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_READER), reason="the reference tree is only present in the build container")
+def test_the_reference_reader_reads_our_files(tmp_path, monkeypatch):
+    """The reference's own post-processing reader (utils/read_binary_data/python/read_single_field_binary.py,
+    the one its tests/*/test.py use) on the geometry, grid and field files written here."""
+    import sys
+    monkeypatch.syspath_prepend(REF_READER)
+    sys.modules.pop("read_single_field_binary", None)
+    from read_single_field_binary import read_single_field_binary
+    case = cases.make("channel", str(tmp_path / "run"), fft_axis=2)
+    out = tmp_path / "data"
+    load.save_geometry(str(out), case)
+    blk = case.params.blocks[0]
+    ng = tuple(int(x) for x in blk.ng)
+    full = np.random.default_rng(21).standard_normal(ng)
+    for box in case.world.boxes:   # every box of the block writes its own part
+        p = np.zeros(tuple(int(x) + 2 for x in box.n), order="F")
+        lo1, hi1 = box.lo, box.hi   # one block starting at (1,1,1): block-local = global
+        p[1:-1, 1:-1, 1:-1] = full[lo1[0] - 1:hi1[0], lo1[1] - 1:hi1[1], lo1[2] - 1:hi1[2]]
+        load.out3d(str(out / "vex_fld_0000010_b_001.bin"), ng, lo1, hi1, p)
+    monkeypatch.chdir(out)
+    data, xp, yp, zp, xu, yv, zw = read_single_field_binary("vex_fld_0000010_b_001.bin", 1, np.array([1, 1, 1]))
+    assert np.array_equal(data, full)
+    g = case.bgrids[0]
+    assert np.array_equal(xp, g[0].rc[1:-1]) and np.array_equal(xu, g[0].rf[1:-1])
+    assert np.array_equal(zp, g[2].rc[1:-1]) and np.array_equal(zw, g[2].rf[1:-1])
