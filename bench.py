@@ -39,7 +39,7 @@ METRIC = "Mpts*step/s (RK3 step of the pressure-correction pipeline)"
 
 # algorithmic HBM bytes per grid point and launch of each kernel class
 ALG_BYTES = {"rk_mom": 96.0, "fillps": 32.0, "fft_fwd": 16.0, "fft_bwd": 16.0, "correc_updt_pressure": 72.0,
-             "mg_down_l0": 26.0, "mg_up_l0": 26.0, "direct_transform": 16.0, "direct_tridiag": 24.0}
+             "mg_down_l0": 26.0, "mg_up_l0": 26.0, "direct_transform": 16.0, "direct_tridiag": 48.0}
 
 
 # ---- workloads ---------------------------------------------------------------------------------

@@ -311,6 +311,12 @@ static void commit(Ctx &ctx) {
     for (int s = 0; s < ctx.prm.nscal; ++s) { alloc_field(ctx, b.s[s], b.g, r, AK_S0 + s); b.ds[s].alloc(b.g); }
     if (ctx.prm.nscal > 0) { b.scr0.alloc(b.g); b.scr1.alloc(b.g); }
     compute_bc_rhs(ctx, b);
+    b.tma_ok = true;
+    for (int q = 0; q < 2 && b.tma_ok; ++q) {
+      b.tma_ok = mom_tma_make_map(b.tmap[q][0], b.u[q].p, b.g) && mom_tma_make_map(b.tmap[q][1], b.v[q].p, b.g) &&
+                 mom_tma_make_map(b.tmap[q][2], b.w[q].p, b.g);
+    }
+    b.tma_ok = b.tma_ok && mom_tma_make_map(b.tmap[0][3], b.p.p, b.g);
     if (ctx.comm.nproc > 1) {   // landing buffers of the x-faces pushed by neighbours on other processes (bound.cu)
       std::vector<int> fkeys = {AK_U0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P};
       if (!b.pp_is_po) fkeys.push_back(AK_PP);
@@ -410,7 +416,15 @@ static void commit(Ctx &ctx) {
         s.b = b.rhs.p;
       }
     }
-    S.setup(ctx, std::move(sb), batched);
+    // separable planes (one rectangle per plane with a uniform, transformable direction): the direct solver
+    // replaces the multigrid cycle; the hierarchy is then not built (level 0 only holds the arrays)
+    int tdir = -1;
+    if (batched && !ctx.prm.mg_generic && ctx.prm.plane_solver != 1) tdir = direct_pick(sb, true, ctx.local_of_rank);
+    if (ctx.prm.plane_solver == 2 && tdir < 0)
+      throw Error("plane_solver = direct: the 2-D problems are not separable (planes split over blocks, or no uniform "
+                  "periodic/Neumann/Dirichlet direction); use the multigrid");
+    S.setup(ctx, std::move(sb), batched, tdir >= 0 ? 1 : 24);
+    if (tdir >= 0) { S.direct.setup(ctx, S, tdir); ctx.direct_on = true; }
   }
   if (ctx.prm.impdiff) setup_impdiff(ctx);
   ctx.red.alloc(8);
@@ -583,7 +597,8 @@ static void do_rk_mom(Ctx &ctx, int irk, double dt) {
   double pts = 0.0;
   for (auto &b : ctx.boxes) pts += (double)b->g.n[0] * b->g.n[1] * b->g.n[2];
   ProfScope ps(ctx, PC_RK_MOM, pts);
-  for (auto &b : ctx.boxes) launch_rk_mom(ctx, *b, irk, dt);
+  for (auto &b : ctx.boxes)
+    if (!launch_rk_mom_tma(ctx, *b, irk, dt)) launch_rk_mom(ctx, *b, irk, dt);
   ctx.par = 1 - ctx.par;
 }
 static void do_bounduvw(Ctx &ctx, bool is_correc) {
@@ -1139,7 +1154,8 @@ int snac_profile_units(snac_handle *h, int cls, double *points) {
 }
 const char *snac_profile_name(int cls) {
   static const char *names[PC_COUNT] = {"rk_mom", "halo_bc", "fillps", "fft_fwd", "mg_smooth_l0", "mg_down_l0",
-                                        "mg_up_l0", "mg_coarse_levels", "fft_bwd", "correc_updt_pressure", "chkdt_chkdiv"};
+                                        "mg_up_l0", "mg_coarse_levels", "fft_bwd", "correc_updt_pressure", "chkdt_chkdiv",
+                                        "direct_transform", "direct_tridiag"};
   return (cls >= 0 && cls < PC_COUNT) ? names[cls] : nullptr;
 }
 int snac_timer_start(snac_handle *h) { SNAC_TRY(h, SNAC_CUDA(cudaEventRecord(h->ctx.timer_ev[0], h->ctx.stream))) }

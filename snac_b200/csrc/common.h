@@ -322,7 +322,27 @@ struct SBox {
   int qqq[3] = {0, 0, 0};           // 1: unknowns staggered along that direction (src/solver.f90:66-67)
 };
 
+// direct solver of separable planes (direct.cu)
+struct TriArgs;
+struct MGSolver;
+struct DirectBox {
+  R2RPlan plan;            // transform along the uniform direction of the plane
+  Dev1 mu, stab;           // its eigenvalues / h^2; the 1-D operator of the other direction
+  DevBuf ib, ie, ig;       // factorisation: 1/pivot (slab layout), coupling to the last unknown (cyclic), 1/g
+  bool cyclic = false;
+};
+struct DirectSolver {
+  bool on = false;
+  int tdir = 0;            // plane direction that is transformed (0 or 1)
+  std::vector<DirectBox> box;
+  void setup(Ctx &ctx, MGSolver &S, int tdir);
+  void solve(Ctx &ctx, MGSolver &S);
+  TriArgs args(const MGSolver &S, int lb, double alpha) const;
+};
+int direct_pick(const std::vector<SBox> &sboxes, bool ids_local, const std::vector<int> &local_of_rank);
+
 struct MGSolver {
+  DirectSolver direct;
   int fft_dir = -1;                // uncoupled direction in solver order (2 when batched) or -1
   int perm[3] = {0, 1, 2};         // solver direction -> physical direction
   std::vector<Field3> x0, b0;      // owned level-0 arrays (batched layout)
@@ -401,6 +421,10 @@ struct Box {
   double cbp[3][2];
   Dev1 inflow[3][2][3];     // inflow planes [idir][ib][component u,v,w] (u_in/v_in/w_in%{x,y,z}, src/main.f90:232-240)
   bool is_inflow[3][2] = {{false, false}, {false, false}, {false, false}};
+  // TMA tensor maps (CUtensorMap, 128 bytes each) of u,v,w per velocity buffer and of p ([0][3]) for the z-marching
+  // rk_mom kernel (mom_tma.cu); tma_ok: they could be encoded
+  alignas(64) unsigned char tmap[2][4][128];
+  bool tma_ok = false;
   bool pp_is_po = false;    // 3-D solve: pp aliases the solver iterate
   double *pp_ptr() const { return pp_is_po ? po.p : pp.p; }
   BoxGeom geom() const;
@@ -456,7 +480,7 @@ struct PeerComm {
 // per-kernel-class device timing (enabled by snac_profile_enable; serialises the stream)
 enum ProfClass : int {
   PC_RK_MOM = 0, PC_HALO_BC, PC_FILLPS, PC_FFT_FWD, PC_MG_SMOOTH0, PC_MG_DOWN0, PC_MG_UP0, PC_MG_COARSE,
-  PC_FFT_BWD, PC_CORREC, PC_CHK, PC_COUNT
+  PC_FFT_BWD, PC_CORREC, PC_CHK, PC_DIRECT_TRANSFORM, PC_DIRECT_TRIDIAG, PC_COUNT
 };
 
 struct Ctx {
@@ -531,6 +555,8 @@ struct ProfScope {
 
 // mom.cu / pois.cu entry points (one call handles one box)
 void launch_rk_mom(Ctx &ctx, Box &b, int irk, double dt);
+bool launch_rk_mom_tma(Ctx &ctx, Box &b, int irk, double dt);   // mom_tma.cu; false: not applicable, use launch_rk_mom
+bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g);
 void launch_fillps(Ctx &ctx, Box &b, double dtrk);
 void launch_fillps_bc(Ctx &ctx, Box &b, double dtrk);
 void launch_updt_rhs(Ctx &ctx, Box &b);

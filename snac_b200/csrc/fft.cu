@@ -19,6 +19,7 @@
 
 #include "common.h"
 #include "fft_radix.cuh"
+#include "fft_row.cuh"
 
 namespace snac {
 
@@ -475,6 +476,14 @@ void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const do
   const long ntiles = (long)((n3[a.pd] + tp - 1) / tp) * n3[a.od];
   const size_t smem = (size_t)n * (tp + 1) * sizeof(double);
   static const bool staged_only = getenv("SNAC_FFT_STAGED") && atoi(getenv("SNAC_FFT_STAGED")) != 0;   // test hook
+  if (pl.fast && a.in_lane_t && a.out_lane_t && !staged_only) {   // the axis is contiguous on both sides: one warp per row
+    a.tab = pl.twiddle.p();
+    if (rowfft::row_launch(ctx.stream, a, dir)) {
+      ctx.launches++;
+      SNAC_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   if (pl.fast && !a.in_lane_t && !a.out_lane_t && !staged_only) {
     a.tab = pl.twiddle.p();
     a.tp = radix::TP;

@@ -659,7 +659,7 @@ struct Cycle {
 }  // namespace
 
 void MGSolver::stats(Ctx &ctx, int *iters, double *relres, double *mean_iters) {
-  if (plane_local) {
+  if (plane_local && !direct.on) {
     std::vector<int> it(nq);
     std::vector<double> rel(nq);
     SNAC_CUDA(cudaMemcpyAsync(it.data(), d_iters, nq * sizeof(int), cudaMemcpyDeviceToHost, ctx.stream));
@@ -786,6 +786,7 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
 }
 
 void MGSolver::solve(Ctx &ctx) {
+  if (direct.on) { direct.solve(ctx, *this); return; }
   int npre, npost;
   mg_sweeps(ctx, *this, npre, npost);
   Cycle cy{ctx, *this, {fft_dir != 0, fft_dir != 1, fft_dir != 2}, npre, npost,

@@ -221,10 +221,11 @@ def test_solver_two_sweeps_on_stretched_planes(tmp_path, kind, fa, kw):
     _solve_and_compare(tmp_path, kind, fa, kw, False, sweeps=2)
 
 
-def _solve_and_compare(tmp_path, kind, fa, kw, generic, sweeps=0):
-    case = cases.make(kind, str(tmp_path), fft_axis=fa, **kw)
+def _solve_and_compare(tmp_path, kind, fa, kw, generic, sweeps=0, solver="mg", case=None):
+    case = case if case is not None else cases.make(kind, str(tmp_path), fft_axis=fa, **kw)
     fields = cases.random_fields(case, seed=7)
-    o, g = make_pair(case, fields, tol=1e-11, maxiter=200, mg_generic=generic, mg_npre=sweeps, mg_npost=sweeps)
+    o, g = make_pair(case, fields, tol=1e-11, maxiter=200, mg_generic=generic, mg_npre=sweeps, mg_npost=sweeps, solver=solver)
+    assert g.solver_name() == ("direct" if solver == "direct" else "mg")
     o.bounduvw(False)
     o.dt = 0.01
     dtrk = float(RK[0].sum()) * o.dt
