@@ -4,7 +4,7 @@
 // Same arithmetic as rk_mom_kernel (mom.cu; reference rk_mom src/rk.f90:7-128, mom{x,y,z}_a_vv src/mom.f90:112-219,
 // _d :221-327, _p :328-386), different data movement.  A CTA owns an x-y tile of TX x TY cells and marches over
 // a chunk of z-planes; a single thread issues, NS-2 planes ahead of their use, one cp.async.bulk.tensor (TMA) box
-// load per field and plane -- the (TX+2) x (TY+2) tile of u, v, w and p with its halo -- into a ring of NS
+// load per field and plane -- the tile of u, v, w and p with its halo -- into a ring of NS
 // shared-memory slots, completion signalled on one mbarrier per slot.  The stencil reads its in-plane neighbours
 // from the slots of planes k and k+1; everything it needs from plane k-1 (u, v, w at the cell, w at i+1 and at
 // j+1) it already holds in registers from the previous step, which also hand u0/uim/v0/vjm/w0/p0 from k+1 to k.
@@ -21,7 +21,10 @@ namespace snac {
 namespace {
 
 constexpr int TX = 32, TY = 8;            // cells per tile = threads per CTA (one cell each per plane)
-constexpr int BX = TX + 2, BY = TY + 2;   // tile with halo
+// tile with halo.  TMA wants the first element of a box row 16-byte aligned in global memory; the arrays put the
+// first INTERIOR element of a row on a 128-byte boundary (Grid3), so the halo column i0-1 sits 8 bytes before one:
+// the box starts one element further left (i0-2, never used) and is TX+4 wide.
+constexpr int BX = TX + 4, BY = TY + 2;
 constexpr int BUF = ((BX * BY * 8 + 127) / 128) * 128 / 8;   // doubles per field and slot (128-byte aligned for TMA)
 #ifndef SNAC_MOM_NS
 #define SNAC_MOM_NS 8
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__(TX * TY, 2) rk_mom_tma_kernel(const __grid_con
 #pragma unroll
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the barriers are visible to the TMA unit
   }
   __syncthreads();
   // planes k0-1 .. k1+1 are needed; plane p (numbered from k0-1 = 0) lives in slot p mod NS
@@ -87,10 +91,10 @@ __global__ void __launch_bounds__(TX * TY, 2) rk_mom_tma_kernel(const __grid_con
     double *dst = ring + (size_t)s * 4 * BUF;
     mbar_expect_tx(&full[s], SLOT_BYTES);
     const int kk = k0 - 1 + p;
-    tma_load_3d(dst, &tm_u, &full[s], i0, j0 - 1, kk);
-    tma_load_3d(dst + BUF, &tm_v, &full[s], i0, j0 - 1, kk);
-    tma_load_3d(dst + 2 * BUF, &tm_w, &full[s], i0, j0 - 1, kk);
-    tma_load_3d(dst + 3 * BUF, &tm_p, &full[s], i0, j0 - 1, kk);
+    tma_load_3d(dst, &tm_u, &full[s], i0 - 1, j0 - 1, kk);            // coordinate = index + 1 (see mom_tma_make_map): i0-2
+    tma_load_3d(dst + BUF, &tm_v, &full[s], i0 - 1, j0 - 1, kk);
+    tma_load_3d(dst + 2 * BUF, &tm_w, &full[s], i0 - 1, j0 - 1, kk);
+    tma_load_3d(dst + 3 * BUF, &tm_p, &full[s], i0 - 1, j0 - 1, kk);
   };
   if (tid == 0)
     for (int p = 0; p < min(NS, np); ++p) issue(p);
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(TX * TY, 2) rk_mom_tma_kernel(const __grid_con
   const double rdyf_j = __ldg(a.rdf[1] + jc), rdyf_jp = __ldg(a.rdf[1] + jc + 1);
   const double rdxc_i = __ldg(a.rdc[0] + ic), rdxc_im = __ldg(a.rdc[0] + ic - 1);
   const double rdyc_j = __ldg(a.rdc[1] + jc), rdyc_jm = __ldg(a.rdc[1] + jc - 1);
-  const int o = (ty + 1) * BX + tx + 1;                  // the cell inside a tile
+  const int o = (ty + 1) * BX + tx + 2;                  // the cell inside a tile
   const long c0 = ic + a.sy * jc;
 
   // prologue: plane k0-1 (what a step inherits from "k-1") and the centre values of plane k0
@@ -207,9 +211,10 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
-// Tensor map of one ghosted field for the (TX+2) x (TY+2) x 1 tiles of rk_mom_tma_kernel.  The map starts one
+// Tensor map of one ghosted field for the BX x BY x 1 tiles of rk_mom_tma_kernel.  The map starts one
 // element before the (0,0,0) corner: that address is 16-byte aligned (Field3: the corner sits 15 doubles into a
-// 256-byte aligned allocation), so element (i,j,k) has the coordinates (i+1, j, k).
+// 256-byte aligned allocation), so element (i,j,k) has the coordinates (i+1, j, k) and boxes start at even
+// coordinates.
 bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
