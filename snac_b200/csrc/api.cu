@@ -91,6 +91,7 @@ static void build_cen_bc(Ctx &ctx, FaceFill &ff, double *(*get)(Box &, int), int
 // block-level description used by the batched solver: the boxes of a block are merged so that
 // every 2-D problem lives on one array per block (the transform kernels scatter/gather the pieces)
 struct BlockInfo {
+  std::vector<int> members;   // ids of the blocks merged into this one (merge_blocks), first = id
   int id;
   int lo_g[3], hi_g[3];
   int nb[3][2];         // neighbour block or -1
@@ -109,6 +110,7 @@ static std::vector<BlockInfo> assemble_blocks(Ctx &ctx) {
       index_of[w.block] = (int)blocks.size();
       BlockInfo B;
       B.id = w.block;
+      B.members.assign(1, w.block);
       for (int d = 0; d < 3; ++d) {
         B.lo_g[d] = w.lo[d]; B.hi_g[d] = w.hi[d];
         for (int ib = 0; ib < 2; ++ib) { B.nb[d][ib] = -1; B.face_rank[d][ib] = -1; }
@@ -142,6 +144,75 @@ static std::vector<BlockInfo> assemble_blocks(Ctx &ctx) {
         B.nb[d][ib] = nbr < 0 ? -1 : index_of[ctx.world[nbr].block];
       }
   return blocks;
+}
+
+// Friend blocks whose union is one rectangle are one block as far as the 2-D solves are concerned: the matrix rows
+// of init_matrix_2d (src/solver.f90:687-842) couple the cells across a friend face exactly as they couple cells
+// inside a block (the halo of the neighbour carries the unknown, spacings come from bound_grid), so the per-wavenumber
+// problem of e.g. the reference's 2 x 2-block duct (examples/_manuscript_turbulent_duct, periodic_duct) is the
+// problem of one block cut differently.  Merged, its planes are whole in the slab layout: the plane-local
+// multigrid kernels and the direct solver apply, on any number of GPUs, and no block-interface exchange is left in
+// the solver.  Returns the blocks unchanged unless ALL of them tile their bounding box, the 1-D grids agree where
+// blocks overlap in index space and every outer face carries one boundary condition.
+static std::vector<BlockInfo> merge_blocks(Ctx &ctx, const std::vector<BlockInfo> &blocks) {
+  const bool off = getenv("SNAC_MERGE_BLOCKS") && atoi(getenv("SNAC_MERGE_BLOCKS")) == 0;   // test hook: keep the general path
+  if (blocks.size() < 2 || off) return blocks;
+  BlockInfo M;
+  M.id = blocks[0].id;
+  for (const BlockInfo &B : blocks) { M.members.push_back(B.id); M.id = std::min(M.id, B.id); }
+  double vol = 0.0;
+  for (int d = 0; d < 3; ++d) { M.lo_g[d] = blocks[0].lo_g[d]; M.hi_g[d] = blocks[0].hi_g[d]; }
+  for (const BlockInfo &B : blocks) {
+    double v = 1.0;
+    for (int d = 0; d < 3; ++d) {
+      M.lo_g[d] = std::min(M.lo_g[d], B.lo_g[d]); M.hi_g[d] = std::max(M.hi_g[d], B.hi_g[d]);
+      v *= B.hi_g[d] - B.lo_g[d] + 1;
+    }
+    vol += v;
+  }
+  double box = 1.0;
+  for (int d = 0; d < 3; ++d) box *= M.hi_g[d] - M.lo_g[d] + 1;
+  if (vol != box) return blocks;   // holes or overlaps: not a rectangle
+  for (int d = 0; d < 3; ++d) {
+    const int N = M.hi_g[d] - M.lo_g[d] + 1;
+    M.dc[d].assign(N + 2, 0.0); M.df[d].assign(N + 2, 0.0);
+    std::vector<char> set(N + 2, 0);
+    for (const BlockInfo &B : blocks) {
+      const int n = B.hi_g[d] - B.lo_g[d] + 1, o = B.lo_g[d] - M.lo_g[d];
+      for (int q = 0; q <= n + 1; ++q) {
+        // a block's ghost entries (q = 0, n+1) are only authoritative on the outer faces of the union
+        const bool ghost = q == 0 || q == n + 1;
+        if (ghost && !((q == 0 && o == 0) || (q == n + 1 && o + n == N))) {
+          if (q == 0) { if (!set[o]) { M.dc[d][o] = B.dc[d][0]; } else if (std::fabs(M.dc[d][o] - B.dc[d][0]) > 1e-13 * std::fabs(B.dc[d][0])) return blocks; }
+          continue;
+        }
+        if (set[o + q] && (std::fabs(M.dc[d][o + q] - B.dc[d][q]) > 1e-13 * std::fabs(B.dc[d][q]) ||
+                           std::fabs(M.df[d][o + q] - B.df[d][q]) > 1e-13 * std::fabs(B.df[d][q])))
+          return blocks;
+        M.dc[d][o + q] = B.dc[d][q]; M.df[d][o + q] = B.df[d][q];
+        set[o + q] = 1;
+      }
+    }
+    for (int ib = 0; ib < 2; ++ib) {
+      // all blocks on this outer face: same kind (physical with one condition, or periodic onto the union)
+      M.face_rank[d][ib] = -1;
+      int kind = -2;   // -1 physical, >= 0 periodic
+      for (const BlockInfo &B : blocks) {
+        const bool outer = ib == 0 ? B.lo_g[d] == M.lo_g[d] : B.hi_g[d] == M.hi_g[d];
+        if (!outer) { if (B.nb[d][ib] < 0) return blocks; continue; }   // an inner face must have a friend
+        const int fr = B.face_rank[d][ib];
+        const int k = B.nb[d][ib] < 0 ? -1 : 0;
+        if (kind == -2) { kind = k; M.face_rank[d][ib] = fr; }
+        else if (kind != k) return blocks;
+        else if (ctx.world[fr].dl[d][ib] != ctx.world[M.face_rank[d][ib]].dl[d][ib] ||
+                 (k < 0 && (ctx.world[fr].cbcpre[d][ib] != ctx.world[M.face_rank[d][ib]].cbcpre[d][ib] ||
+                            ctx.world[fr].bcpre[d][ib] != ctx.world[M.face_rank[d][ib]].bcpre[d][ib])))
+          return blocks;   // (on 'F' faces bcpre holds the friend block's number, which differs from block to block)
+      }
+      M.nb[d][ib] = kind >= 0 ? 0 : -1;   // periodic wrap onto the merged block itself (index 0)
+    }
+  }
+  return std::vector<BlockInfo>(1, M);
 }
 
 // Which wavenumbers does process `proc` solve?  Cyclic (q mod nproc == proc) when the number of
@@ -262,7 +333,7 @@ static void commit(Ctx &ctx) {
   const bool batched = ctx.prm.fft_axis > 0;
   const int nl = (int)ctx.boxes.size();
   std::vector<BlockInfo> blocks;
-  if (batched) blocks = assemble_blocks(ctx);
+  if (batched) blocks = merge_blocks(ctx, assemble_blocks(ctx));
   ctx.nq = batched ? ctx.boxes[0]->g.n[fa] : 1;
   q_range(ctx, ctx.nq, ctx.comm.me, ctx.q0, ctx.q1);
   if (batched && ctx.q1 <= ctx.q0) throw Error("more processes than wavenumbers: nothing to solve on this process");
@@ -352,8 +423,10 @@ static void commit(Ctx &ctx) {
       ctx.block_index.assign(1, -1);
       for (size_t ib_ = 0; ib_ < blocks.size(); ++ib_) {
         BlockInfo &B = blocks[ib_];
-        if ((int)ctx.block_index.size() <= B.id) ctx.block_index.resize(B.id + 1, -1);
-        ctx.block_index[B.id] = (int)ib_;
+        for (int mid : B.members) {
+          if ((int)ctx.block_index.size() <= mid) ctx.block_index.resize(mid + 1, -1);
+          ctx.block_index[mid] = (int)ib_;
+        }
         SBox &s = sb[ib_];
         const snac_box &w0 = ctx.world[B.face_rank[fa][0]];
         for (int sd = 0; sd < 3; ++sd) {
@@ -390,7 +463,8 @@ static void commit(Ctx &ctx) {
         }
       }
       ctx.blocks_lo.clear();
-      for (BlockInfo &B : blocks) ctx.blocks_lo.push_back({B.lo_g[0], B.lo_g[1], B.lo_g[2]});
+      ctx.blocks_id.clear();
+      for (BlockInfo &B : blocks) { ctx.blocks_lo.push_back({B.lo_g[0], B.lo_g[1], B.lo_g[2]}); ctx.blocks_id.push_back(B.id); }
     } else {
       sb.resize(nl);
       for (int lb = 0; lb < nl; ++lb) {
@@ -502,12 +576,12 @@ static void finish_setup(Ctx &ctx) {
         q_range(ctx, ctx.nq, p, q0, q1);
         double *xb, *bb;
         if (p == ctx.comm.me) { xb = S.xcur(bi); bb = S.bcur(bi); }
-        else { xb = ctx.comm.remote(p, b.info.block, AK_SLAB_X) + 15; bb = ctx.comm.remote(p, b.info.block, AK_SLAB_B) + 15; }
+        else { xb = ctx.comm.remote(p, ctx.blocks_id[bi], AK_SLAB_X) + 15; bb = ctx.comm.remote(p, ctx.blocks_id[bi], AK_SLAB_B) + 15; }
         // every array the owner's iterate can move to (the owner's own ones are looked up when they are needed)
         static const int slot_keys[4] = {AK_SLAB_X, AK_SLAB_X1, AK_SLAB_K1, AK_SLAB_K2};
         for (int sl = 0; sl < 4; ++sl)
           R.xs[p][sl] = (p == ctx.comm.me || ctx.comm.nproc == 1) ? nullptr
-                        : ctx.comm.remote(p, b.info.block, slot_keys[sl]) + 15 + off - (q_is_cyclic(ctx) ? 0 : (long)q0 * sg.st(2));
+                        : ctx.comm.remote(p, ctx.blocks_id[bi], slot_keys[sl]) + 15 + off - (q_is_cyclic(ctx) ? 0 : (long)q0 * sg.st(2));
         // chunks: the wavenumber index is absolute in the kernels, shift by the slab origin; cyclic: the
         // kernels divide the index by the number of processes themselves
         const long shift = q_is_cyclic(ctx) ? 0 : (long)q0 * sg.st(2);

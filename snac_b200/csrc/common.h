@@ -506,6 +506,7 @@ struct Ctx {
   bool q_cyclic = false;                    // ... which are q0 + k nproc (cyclic) instead of q0 + k
   std::vector<int> block_index;             // block id -> solver box
   std::vector<std::array<int, 3>> blocks_lo;
+  std::vector<int> blocks_id;               // solver box -> id under which its slabs are published (first member block)
   std::vector<FFTRoute> route;              // per local box
   int par = 0;                              // which velocity buffer is current
   double prev_dtrk = 0.0;                   // sub-step size of the previous pressure solve (initial-guess scaling)

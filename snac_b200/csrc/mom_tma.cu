@@ -20,7 +20,13 @@ namespace snac {
 
 namespace {
 
-constexpr int TX = 32, TY = 8;            // cells per tile = threads per CTA (one cell each per plane)
+#ifndef SNAC_MOM_TY
+#define SNAC_MOM_TY 8
+#endif
+#ifndef SNAC_MOM_MINB
+#define SNAC_MOM_MINB 2
+#endif
+constexpr int TX = 32, TY = SNAC_MOM_TY;  // cells per tile = threads per CTA (one cell each per plane)
 // tile with halo.  TMA wants the first element of a box row 16-byte aligned in global memory; the arrays put the
 // first INTERIOR element of a row on a 128-byte boundary (Grid3), so the halo column i0-1 sits 8 bytes before one:
 // the box starts one element further left (i0-2, never used) and is TX+4 wide.
@@ -66,7 +72,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 
 template <bool IMPDIFF, bool FIRST>
-__global__ void __launch_bounds__(TX * TY, 2) rk_mom_tma_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
+__global__ void __launch_bounds__(TX * TY, SNAC_MOM_MINB) rk_mom_tma_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
                                                                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_p,
                                                                const MomTmaArgs a) {
   extern __shared__ __align__(128) double ring[];   // [NS][4][BUF]

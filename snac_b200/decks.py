@@ -105,6 +105,26 @@ def duct_blocks_case(rundir, n=(8, 8, 8), **kw):
     write_case(rundir, blocks, **kw)
 
 
+def lshape_blocks_case(rundir, n=(8, 8, 8), **kw):
+    """Three friend blocks forming an L in the y-z cross-section (x periodic, walls outside): a multi-block
+    geometry that is NOT a rectangle, so the planes of the per-wavenumber problems stay split over blocks and the
+    solver has to couple them through the block interfaces (general multigrid path)."""
+    nx, ny, nz = n
+    #            y-   y+   z-   z+
+    lay = {1: ("N", "F", "N", "F", (0.0, 0.0)),    # corner block: friends 2 (y+) and 3 (z+)
+           2: ("F", "N", "N", "N", (0.5, 0.0)),    # right arm
+           3: ("N", "N", "F", "N", (0.0, 0.5))}    # upper arm
+    fr = {1: [1, 1, 1, 2, 1, 3], 2: [2, 2, 1, 2, 2, 2], 3: [3, 3, 3, 3, 1, 3]}
+    blocks = []
+    for ib in (1, 2, 3):
+        ym, yp, zm, zp, (y0, z0) = lay[ib]
+        pre = ["F", "F", ym, yp, zm, zp]
+        vel = ["F" if c == "F" else "D" for c in pre]
+        blocks.append(dict(dims=(1, 1, 1), ng=(nx, ny, nz), lmin=(0.0, y0, z0), lmax=(1.0, y0 + 0.5, z0 + 0.5), friends=fr[ib],
+                           cbcvel=["".join(vel)] * 3, cbcpre="".join(pre), inivel="poi"))
+    write_case(rundir, blocks, **kw)
+
+
 def developing_channel_case(rundir, ng=(16, 8, 12), dims=(2, 1, 2), inflow=1, **kw):
     """The reference's examples/developing_channel topology (inflow at x-, outflow with p = 0 at x+, y periodic,
     walls in z) with an inflow plane of the given type on x- (src/main.f90:594-632; 1 = Poiseuille)."""
@@ -122,7 +142,7 @@ def make(kind, rundir, fft_axis=0, impdiff=False, boussinesq=False, **kw):
         kw.setdefault("dims", (1, 2, 2))
     if kind == "cavity" and fft_axis == 2:
         kw.setdefault("dims", (2, 1, 1))
-    {"channel": channel_case, "cavity": cavity_case, "tgv": tgv_case, "duct": duct_blocks_case,
+    {"channel": channel_case, "cavity": cavity_case, "tgv": tgv_case, "duct": duct_blocks_case, "lshape": lshape_blocks_case,
      "devchannel": developing_channel_case}[kind](rundir, **kw)
     return setup_case(rundir, fft_axis=fft_axis, impdiff=impdiff, boussinesq=boussinesq)
 

@@ -59,7 +59,7 @@ def test_direct_solver_transform_along_the_second_plane_direction(tmp_path):
 
 def test_direct_solver_refuses_planes_that_are_not_separable(tmp_path):
     from snac_b200.sim import Simulation
-    case = cases.make("duct", str(tmp_path / "a"), fft_axis=1)        # planes split over four friend blocks
+    case = cases.make("lshape", str(tmp_path / "a"), fft_axis=1)      # planes split over three friend blocks (an L)
     with pytest.raises(L.SnacError, match="not separable"):
         Simulation(case, solver="direct")
     g = Simulation(case, solver="auto")
@@ -71,7 +71,14 @@ def test_direct_solver_refuses_planes_that_are_not_separable(tmp_path):
     g.close()
 
 
-@pytest.mark.parametrize("kind,fa,kw", [("channel", 2, {}), ("tgv", 3, dict(n=16)), ("channel", 1, {})])
+def test_friend_blocks_tiling_a_rectangle_are_solved_as_one_block(tmp_path):
+    """the reference's 2 x 2-block duct: the union of the blocks is a rectangle, the 2-D problems are those of one
+    block (api.cu merge_blocks), so the direct solver applies; the result is the exact solution of the 4-block system"""
+    _solve_and_compare(tmp_path, "duct", 1, {}, False, solver="direct")
+    _solve_and_compare(tmp_path / "b", "duct", 1, dict(n=(16, 12, 10)), False, solver="direct")
+
+
+@pytest.mark.parametrize("kind,fa,kw", [("channel", 2, {}), ("tgv", 3, dict(n=16)), ("channel", 1, {}), ("duct", 1, {})])
 def test_direct_solver_three_steps_against_the_oracle(tmp_path, kind, fa, kw):
     case = cases.make(kind, str(tmp_path), fft_axis=fa, **kw)
     ini = initial_fields(case, noise=(kind != "tgv"))

@@ -49,7 +49,7 @@ def cmp_uvw(o, g, tol, interior=False):
             assert d <= tol * n or d == 0.0, (k, r, d / n if n > 0 else d)
 
 
-CASES = [("channel", 0), ("channel", 1), ("channel", 2), ("cavity", 0), ("cavity", 2), ("duct", 0), ("duct", 1),
+CASES = [("channel", 0), ("channel", 1), ("channel", 2), ("cavity", 0), ("cavity", 2), ("duct", 0), ("duct", 1), ("lshape", 1),
          ("tgv", 3)]
 
 
@@ -178,6 +178,8 @@ def test_long_transforms_match_fftw_definitions(tmp_path, n, axis, bc01):
 # (kind, fft_axis, extra case arguments, force the general multi-box kernels)
 SOLVE_CASES = [("channel", 0, {}, False), ("channel", 1, {}, False), ("channel", 2, {}, False),
                ("cavity", 0, {}, False), ("cavity", 2, {}, False), ("duct", 0, {}, False), ("duct", 1, {}, False),
+               # friend blocks that do not tile a rectangle: planes split over blocks, coupled through their interfaces
+               ("lshape", 1, {}, False), ("lshape", 0, {}, False), ("lshape", 1, dict(n=(8, 12, 10)), False),
                ("tgv", 3, dict(n=16), False), ("tgv", 3, dict(n=16), True), ("tgv", 0, dict(n=16), False),
                # one box per plane: the fused shared-memory / tiled kernels
                ("channel", 2, dict(dims=(1, 1, 1)), False), ("channel", 1, dict(dims=(1, 1, 1)), False),
@@ -284,7 +286,7 @@ def _remove_mean(ps, grids):
     return [p[I] - tot / vol for p in ps]
 
 
-STEP_CASES = [("channel", 0, {}), ("channel", 2, {}), ("cavity", 0, {}), ("duct", 1, {}), ("tgv", 3, dict(n=16)),
+STEP_CASES = [("channel", 0, {}), ("channel", 2, {}), ("cavity", 0, {}), ("duct", 1, {}), ("lshape", 1, {}), ("tgv", 3, dict(n=16)),
               ("channel", 2, dict(dims=(1, 1, 1), ng=(96, 8, 80))), ("channel", 1, dict(dims=(1, 1, 1))),
               ("tgv", 1, dict(n=32))]
 
@@ -294,7 +296,7 @@ def test_full_steps_match_oracle(tmp_path, kind, fa, kw):
     """N complete RK3 steps through snac_step vs. the oracle: u,v,w,p relative L2 <= 1e-8
     (north_star tolerance), divergence at round-off level."""
     case = cases.make(kind, str(tmp_path), fft_axis=fa, **kw)
-    ini = initial_fields(case, noise=(kind in ("channel", "duct")))
+    ini = initial_fields(case, noise=(kind in ("channel", "duct", "lshape")))
     o, g = make_pair(case, ini, tol=1e-12, maxiter=200)
     o.init_bc(); g.init_bc()
     o.set_dt(); g.set_dt()
@@ -505,3 +507,10 @@ def test_scalar_boussinesq_impdiff_steps_match_oracle(tmp_path, kind, fa, impdif
         assert np.isfinite(s_lo) and np.isfinite(s_hi) and s_lo < s_hi
     divtot, divmax = g.chkdiv()
     assert divmax < 1e-9
+
+
+def test_duct_blocks_without_merging_go_through_the_block_interfaces(tmp_path, monkeypatch):
+    """the 2 x 2-block duct with the merging of friend blocks switched off: the general multi-box multigrid
+    (halo exchange of the iterate across block interfaces on every level), against the exact solution"""
+    monkeypatch.setenv("SNAC_MERGE_BLOCKS", "0")
+    _solve_and_compare(tmp_path, "duct", 1, {}, False)
