@@ -387,7 +387,8 @@ static void commit(Ctx &ctx) {
       b.tma_ok = mom_tma_make_map(b.tmap[q][0], b.u[q].p, b.g) && mom_tma_make_map(b.tmap[q][1], b.v[q].p, b.g) &&
                  mom_tma_make_map(b.tmap[q][2], b.w[q].p, b.g);
     }
-    b.tma_ok = b.tma_ok && mom_tma_make_map(b.tmap[0][3], b.p.p, b.g);
+    b.tma_ok = b.tma_ok && mom_tma_make_map(b.tmap[0][3], b.p.p, b.g) && mom_tma_make_map(b.tmap_hist[0], b.du.p, b.g, true) &&
+               mom_tma_make_map(b.tmap_hist[1], b.dv.p, b.g, true) && mom_tma_make_map(b.tmap_hist[2], b.dw.p, b.g, true);
     if (ctx.comm.nproc > 1) {   // landing buffers of the x-faces pushed by neighbours on other processes (bound.cu)
       std::vector<int> fkeys = {AK_U0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P};
       if (!b.pp_is_po) fkeys.push_back(AK_PP);

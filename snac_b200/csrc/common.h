@@ -424,6 +424,7 @@ struct Box {
   // TMA tensor maps (CUtensorMap, 128 bytes each) of u,v,w per velocity buffer and of p ([0][3]) for the z-marching
   // rk_mom kernel (mom_tma.cu); tma_ok: they could be encoded
   alignas(64) unsigned char tmap[2][4][128];
+  alignas(64) unsigned char tmap_hist[3][128];   // du, dv, dw (interior tiles)
   bool tma_ok = false;
   bool pp_is_po = false;    // 3-D solve: pp aliases the solver iterate
   double *pp_ptr() const { return pp_is_po ? po.p : pp.p; }
@@ -557,7 +558,7 @@ struct ProfScope {
 // mom.cu / pois.cu entry points (one call handles one box)
 void launch_rk_mom(Ctx &ctx, Box &b, int irk, double dt);
 bool launch_rk_mom_tma(Ctx &ctx, Box &b, int irk, double dt);   // mom_tma.cu; false: not applicable, use launch_rk_mom
-bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g);
+bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g, bool interior = false);
 void launch_fillps(Ctx &ctx, Box &b, double dtrk);
 void launch_fillps_bc(Ctx &ctx, Box &b, double dtrk);
 void launch_updt_rhs(Ctx &ctx, Box &b);

@@ -33,10 +33,14 @@ constexpr int TX = 32, TY = SNAC_MOM_TY;  // cells per tile = threads per CTA (o
 constexpr int BX = TX + 4, BY = TY + 2;
 constexpr int BUF = ((BX * BY * 8 + 127) / 128) * 128 / 8;   // doubles per field and slot (128-byte aligned for TMA)
 #ifndef SNAC_MOM_NS
-#define SNAC_MOM_NS 8
+#define SNAC_MOM_NS 6
 #endif
 constexpr int NS = SNAC_MOM_NS;           // ring slots: planes k and k+1 in use, NS - 2 in flight
 constexpr unsigned SLOT_BYTES = 4u * BX * BY * 8u;
+constexpr int HBUF = TX * TY;             // doubles per RK-history tile (interior only) and slot
+constexpr unsigned HIST_BYTES = 3u * HBUF * 8u;
+template <bool FIRST>
+__host__ __device__ constexpr int slot_doubles() { return 4 * BUF + (FIRST ? 0 : 3 * HBUF); }
 
 struct MomTmaArgs {
   int n[3];
@@ -74,8 +78,10 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 template <bool IMPDIFF, bool FIRST>
 __global__ void __launch_bounds__(TX * TY, SNAC_MOM_MINB) rk_mom_tma_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
                                                                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_p,
-                                                               const MomTmaArgs a) {
-  extern __shared__ __align__(128) double ring[];   // [NS][4][BUF]
+                                                               const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ CUtensorMap tm_dv,
+                                                               const __grid_constant__ CUtensorMap tm_dw, const MomTmaArgs a) {
+  constexpr int SLOT = slot_doubles<FIRST>();
+  extern __shared__ __align__(128) double ring[];   // [NS][u, v, w, p tiles with halo | du, dv, dw interior tiles]
   __shared__ unsigned long long full[NS];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
   const int i0 = 1 + blockIdx.x * TX, j0 = 1 + blockIdx.y * TY;
@@ -94,9 +100,15 @@ __global__ void __launch_bounds__(TX * TY, SNAC_MOM_MINB) rk_mom_tma_kernel(cons
   const int np = k1 - k0 + 3;
   auto issue = [&](int p) {
     const int s = p % NS;
-    double *dst = ring + (size_t)s * 4 * BUF;
-    mbar_expect_tx(&full[s], SLOT_BYTES);
+    double *dst = ring + (size_t)s * SLOT;
+    const bool hist = !FIRST && p >= 1 && p <= np - 2;        // the RK histories of the planes that are updated
+    mbar_expect_tx(&full[s], SLOT_BYTES + (hist ? HIST_BYTES : 0u));
     const int kk = k0 - 1 + p;
+    if (hist) {   // interior tiles: coordinate = index - 1 (mom_tma_make_map with interior = true)
+      tma_load_3d(dst + 4 * BUF, &tm_du, &full[s], i0 - 1, j0, kk);
+      tma_load_3d(dst + 4 * BUF + HBUF, &tm_dv, &full[s], i0 - 1, j0, kk);
+      tma_load_3d(dst + 4 * BUF + 2 * HBUF, &tm_dw, &full[s], i0 - 1, j0, kk);
+    }
     tma_load_3d(dst, &tm_u, &full[s], i0 - 1, j0 - 1, kk);            // coordinate = index + 1 (see mom_tma_make_map): i0-2
     tma_load_3d(dst + BUF, &tm_v, &full[s], i0 - 1, j0 - 1, kk);
     tma_load_3d(dst + 2 * BUF, &tm_w, &full[s], i0 - 1, j0 - 1, kk);
@@ -123,11 +135,10 @@ __global__ void __launch_bounds__(TX * TY, SNAC_MOM_MINB) rk_mom_tma_kernel(cons
     const double *s = ring;
     ukm = s[o]; vkm = s[BUF + o]; wkm = s[2 * BUF + o]; wipkm = s[2 * BUF + o + 1]; wjpkm = s[2 * BUF + o + BX];
     mbar_wait(&full[1 % NS], 0);
-    const double *t = ring + (size_t)(1 % NS) * 4 * BUF;
+    const double *t = ring + (size_t)(1 % NS) * SLOT;
     u0 = t[o]; uim = t[o - 1]; v0 = t[BUF + o]; vjm = t[BUF + o - BX]; w0 = t[2 * BUF + o]; p0 = t[3 * BUF + o];
   }
-  double hu = 0.0, hv = 0.0, hw = 0.0;
-  if (!FIRST && in) { const long c = c0 + a.sz * k0; hu = a.du[c]; hv = a.dv[c]; hw = a.dw[c]; }
+  const int oh = ty * TX + tx;                            // the cell inside a history tile
   double dzf_k = __ldg(a.df[2] + k0), rdzf_k = __ldg(a.rdf[2] + k0), rdzc_km = __ldg(a.rdc[2] + k0 - 1);
 
   for (int k = k0; k <= k1; ++k) {
@@ -135,13 +146,13 @@ __global__ void __launch_bounds__(TX * TY, SNAC_MOM_MINB) rk_mom_tma_kernel(cons
     // every thread is done with plane p-1 (read last during the previous step): its slot takes plane p-1+NS
     __syncthreads();
     if (tid == 0 && p - 1 + NS < np) issue(p - 1 + NS);
-    const double *sc = ring + (size_t)(p % NS) * 4 * BUF;
-    const double *sn = ring + (size_t)((p + 1) % NS) * 4 * BUF;
+    const double *sc = ring + (size_t)(p % NS) * SLOT;
+    const double *sn = ring + (size_t)((p + 1) % NS) * SLOT;
     mbar_wait(&full[(p + 1) % NS], ((p + 1) / NS) & 1);   // plane p was waited for one step earlier (or in the prologue)
     const double dzf_kp = __ldg(a.df[2] + k + 1), rdzf_kp = __ldg(a.rdf[2] + k + 1), rdzc_k = __ldg(a.rdc[2] + k);
     const long c = c0 + a.sz * k;
-    double hun = 0.0, hvn = 0.0, hwn = 0.0;
-    if (!FIRST && in && k < k1) { hun = a.du[c + a.sz]; hvn = a.dv[c + a.sz]; hwn = a.dw[c + a.sz]; }
+    double hu = 0.0, hv = 0.0, hw = 0.0;
+    if (!FIRST) { hu = sc[4 * BUF + oh]; hv = sc[4 * BUF + HBUF + oh]; hw = sc[4 * BUF + 2 * HBUF + oh]; }
     const double uip = sc[o + 1], ujp = sc[o + BX], ujm = sc[o - BX], uimjp = sc[o + BX - 1];
     const double vip = sc[BUF + o + 1], vim = sc[BUF + o - 1], vjp = sc[BUF + o + BX], vipjm = sc[BUF + o + 1 - BX];
     const double wip = sc[2 * BUF + o + 1], wim = sc[2 * BUF + o - 1], wjp = sc[2 * BUF + o + BX], wjm = sc[2 * BUF + o - BX];
@@ -193,7 +204,6 @@ __global__ void __launch_bounds__(TX * TY, SNAC_MOM_MINB) rk_mom_tma_kernel(cons
     vkm = v0; v0 = vkp; vjm = vjmkp;
     wkm = w0; w0 = wkp; wipkm = wip; wjpkm = wjp;
     p0 = pkp;
-    hu = hun; hv = hvn; hw = hwn;
     dzf_k = dzf_kp; rdzf_k = rdzf_kp; rdzc_km = rdzc_k;
   }
 }
@@ -217,17 +227,19 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
-// Tensor map of one ghosted field for the BX x BY x 1 tiles of rk_mom_tma_kernel.  The map starts one
+// Tensor map of one ghosted field for the BX x BY x 1 tiles of rk_mom_tma_kernel (interior = false) or for the
+// TX x TY x 1 tiles of an RK-history array (interior = true: the map starts at element (1,0,0), which is 128-byte
+// aligned; coordinates = (i-1, j, k)).  The map starts one
 // element before the (0,0,0) corner: that address is 16-byte aligned (Field3: the corner sits 15 doubles into a
 // 256-byte aligned allocation), so element (i,j,k) has the coordinates (i+1, j, k) and boxes start at even
 // coordinates.
-bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g) {
+bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g, bool interior) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t gdim[3] = {(cuuint64_t)g.sy, (cuuint64_t)(g.n[1] + 2), (cuuint64_t)(g.n[2] + 2)};
   const cuuint64_t gstr[2] = {(cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8};
-  const cuuint32_t box[3] = {BX, BY, 1}, estr[3] = {1, 1, 1};
-  void *base = const_cast<double *>(corner) - 1;
+  const cuuint32_t box[3] = {(cuuint32_t)(interior ? TX : BX), (cuuint32_t)(interior ? TY : BY), 1}, estr[3] = {1, 1, 1};
+  void *base = const_cast<double *>(corner) + (interior ? 1 : -1);
   if (reinterpret_cast<size_t>(base) & 15) return false;
   return fn(static_cast<CUtensorMap *>(out128), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -259,10 +271,12 @@ bool launch_rk_mom_tma(Ctx &ctx, Box &b, int irk, double dt) {
   a.kz = (b.g.n[2] + nchunk - 1) / nchunk;
   nchunk = (b.g.n[2] + a.kz - 1) / a.kz;
   dim3 blk(TX, TY, 1), grd((b.g.n[0] + TX - 1) / TX, (b.g.n[1] + TY - 1) / TY, nchunk);
-  const size_t smem = (size_t)NS * 4 * BUF * sizeof(double);
+  const bool imp = ctx.prm.impdiff, first = (a.f2 == 0.0);
+  const size_t smem = (size_t)NS * (first ? slot_doubles<true>() : slot_doubles<false>()) * sizeof(double);
+  const CUtensorMap *th[3] = {reinterpret_cast<const CUtensorMap *>(b.tmap_hist[0]), reinterpret_cast<const CUtensorMap *>(b.tmap_hist[1]),
+                              reinterpret_cast<const CUtensorMap *>(b.tmap_hist[2])};
   const CUtensorMap *tu = reinterpret_cast<const CUtensorMap *>(b.tmap[cur][0]), *tv = reinterpret_cast<const CUtensorMap *>(b.tmap[cur][1]);
   const CUtensorMap *tw = reinterpret_cast<const CUtensorMap *>(b.tmap[cur][2]), *tp = reinterpret_cast<const CUtensorMap *>(b.tmap[0][3]);
-  const bool imp = ctx.prm.impdiff, first = (a.f2 == 0.0);
 #define LAUNCH(I, F)                                                                                                           \
   {                                                                                                                            \
     static bool attr = false;                                                                                                  \
@@ -270,7 +284,7 @@ bool launch_rk_mom_tma(Ctx &ctx, Box &b, int irk, double dt) {
       SNAC_CUDA(cudaFuncSetAttribute(rk_mom_tma_kernel<I, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
       attr = true;                                                                                                             \
     }                                                                                                                          \
-    rk_mom_tma_kernel<I, F><<<grd, blk, smem, ctx.stream>>>(*tu, *tv, *tw, *tp, a);                                            \
+    rk_mom_tma_kernel<I, F><<<grd, blk, smem, ctx.stream>>>(*tu, *tv, *tw, *tp, *th[0], *th[1], *th[2], a);                                            \
   }
   if (imp) { if (first) LAUNCH(true, true) else LAUNCH(true, false) }
   else     { if (first) LAUNCH(false, true) else LAUNCH(false, false) }
