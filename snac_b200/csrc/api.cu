@@ -823,6 +823,7 @@ static void check_peers(Ctx &ctx) {
 __global__ void publish_kernel(const double *vals, double *const *slots, int n, int nproc) {
   const int p = threadIdx.x;
   if (p < nproc) for (int i = 0; i < n; ++i) slots[p][i] = vals[i];
+  __threadfence_system();   // performed at the peers before the kernel completes (the flag is written by a later kernel)
 }
 
 // local reductions, then the MPI_ALLREDUCEs of chkdt/chkdiv (src/chkdt.f90:48, src/chkdiv.f90:42-43):

@@ -13,13 +13,19 @@
 
 namespace snac {
 
-__global__ void copy_ops_kernel(const CopyOp *ops) {
+// remote: some destinations are in a peer's memory.  The flag that tells the peer "the push has arrived" is written by
+// a LATER kernel (comm.cu); a fence in that kernel does not order THESE threads' stores.  Every writer therefore ends
+// with a system-scope fence: its stores have been performed at the peer before the kernel can complete, so the flag
+// cannot overtake the data on the way through the NVLink fabric (seen as a run-to-run varying 1e-3 error with
+// 32^3 boxes on 4 GPUs, where the peer's unpack kernel reads the landing buffer within microseconds of the flag).
+__global__ void copy_ops_kernel(const CopyOp *ops, int remote) {
   const CopyOp op = ops[blockIdx.y];
   const long tot = (long)op.na * op.nb;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
     const int ia = (int)(t % op.na), ib = (int)(t / op.na);
     op.dst[ia * op.dsa + ib * op.dsb] = op.src[ia * op.ssa + ib * op.ssb];
   }
+  if (remote) __threadfence_system();
 }
 
 __global__ void face_ops_kernel(const FaceOp *ops) {
@@ -59,10 +65,10 @@ static int max_plane(const std::vector<T> &v) {
 
 struct OpsMeta { int gx; };
 
-void launch_copy_ops(Ctx &ctx, const DevOps<CopyOp> &ops) {
+void launch_copy_ops(Ctx &ctx, const DevOps<CopyOp> &ops, bool remote) {
   if (!ops.count) return;
   dim3 grd(ops.count ? 64 : 1, ops.count);
-  copy_ops_kernel<<<grd, 256, 0, ctx.stream>>>(ops.d);
+  copy_ops_kernel<<<grd, 256, 0, ctx.stream>>>(ops.d, remote ? 1 : 0);
   ctx.launches++;
 }
 
@@ -152,18 +158,21 @@ void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::ve
 // exchange), copy / push, then wait for the neighbours' pushes
 void Exchange::run(Ctx &ctx, int dir) const {
   if (key0 >= 0) ctx.comm.handshake(ctx, CH_READY, mask[dir]);
-  launch_copy_ops(ctx, local[dir]);
+  launch_copy_ops(ctx, local[dir], key0 >= 0 && mask[dir] != 0);
   if (key0 >= 0) ctx.comm.handshake(ctx, CH_ARRIVED, mask[dir]);
   launch_copy_ops(ctx, unpack[dir]);
 }
 
-void Exchange::run_all(Ctx &ctx) const {   // x, then y, then z (edges/corners propagate)
-  if (key0 >= 0) ctx.comm.handshake(ctx, CH_READY, mask[0] | mask[1] | mask[2]);
-  for (int d = 0; d < 3; ++d) {
-    launch_copy_ops(ctx, local[d]);
-    if (key0 >= 0) ctx.comm.handshake(ctx, CH_ARRIVED, mask[d]);
-    launch_copy_ops(ctx, unpack[d]);
-  }
+// x, then y, then z (edges/corners propagate).  Every direction has its own "ready" handshake: a neighbour may push
+// direction d into this box only after this box has finished directions < d.  The x-faces of a remote neighbour land
+// in a buffer and are scattered into the ghost columns over the FULL y-z extent, ghost planes included (with the
+// stale values the sender had there, exactly as the reference's x-exchange does, src/bound.f90:602-607); the
+// z-push of a remote neighbour then overwrites the edge cells (x-ghost, z-ghost) with the right values.  With one
+// "ready" for all three directions a fast z-neighbour could push BEFORE the x-scatter, which then overwrote the edge
+// with stale data: seen with 32^3 boxes on a 2 x 1 x 2 process grid (errors of 1e-3 at the z-interfaces, gone under
+// CUDA_LAUNCH_BLOCKING); the reference's blocking MPI_SENDRECV per direction implies the same order.
+void Exchange::run_all(Ctx &ctx) const {
+  for (int d = 0; d < 3; ++d) run(ctx, d);
 }
 
 void FaceFill::run(Ctx &ctx) const {

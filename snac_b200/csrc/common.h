@@ -191,7 +191,7 @@ struct FaceFill {
   void run(Ctx &ctx) const;
 };
 
-void launch_copy_ops(Ctx &ctx, const DevOps<CopyOp> &ops);
+void launch_copy_ops(Ctx &ctx, const DevOps<CopyOp> &ops, bool remote = false);
 void launch_face_ops(Ctx &ctx, const DevOps<FaceOp> &ops);
 
 // ------------------------------------------------------------------------------------------

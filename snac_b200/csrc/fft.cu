@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) r2r_dense_kernel(const R2RArgs a) {
       R2R_OUT_AT(t, ob, osa) = acc * a.scale;
     }
   })
+  if (a.out_split) __threadfence_system();   // stores into peers' slabs are performed before the kernel completes (bound.cu)
 }
 
 __device__ inline int brev(int k, int bits) { return (int)(__brev((unsigned)k) >> (32 - bits)); }
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
       }
     })
   }
+  if (a.out_split) __threadfence_system();
 }
 
 // register-radix kernels (fft_radix.cuh): one CTA per tile of 32 pencils
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS) r2r_radix_kernel
     radix::run_pass<R1, R2, false>(a, Zs, T);
     __syncthreads();
     radix::fwd_untangle<R1, R2, SPLIT>(a, Zs, T);
+    if (SPLIT) __threadfence_system();   // the forward transform stores into the owners' slabs, possibly over NVLink
   } else {
     radix::bwd_tangle<R1, R2, SPLIT>(a, Zs, T);
     __syncthreads();
