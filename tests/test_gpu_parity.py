@@ -414,7 +414,9 @@ def test_driver_runs_a_case_directory_like_program_snac(tmp_path):
         assert chk.size == np.prod(ng) + 2 and chk[-1] == 6.0
         assert os.path.exists(os.path.join(data, f"umean_z_fld_0000003_b_{cb}.out"))
         assert os.path.exists(os.path.join(data, f"pmean_x_fld_0000006_b_{cb}.out"))
-        assert len(open(os.path.join(data, f"log_visu_3d_b_{cb}.out")).read().splitlines()) == 4
+        # u,v,w,p of the initial condition (src/main.f90:654-656) and of step 6
+        assert len(open(os.path.join(data, f"log_visu_3d_b_{cb}.out")).read().splitlines()) == 8
+        assert os.path.exists(os.path.join(data, f"umean_z_fld_0000000_b_{cb}.out"))
     sim.close()
 
 
