@@ -263,7 +263,6 @@ static double helm_bc_coef(const Box &b, int d, int ib, char c, double bc, bool 
 
 static void setup_impdiff(Ctx &ctx) {
   if (ctx.prm.fft_axis > 0) throw Error("implicit diffusion together with FFT_AXIS is not available in this build");
-  if (ctx.comm.nproc > 1) throw Error("implicit diffusion on several processes is not available in this build");
   const int nl = (int)ctx.boxes.size();
   auto fold_sign = [](char c, bool centered) {
     if (c == 'N') return 1.0;
@@ -296,7 +295,7 @@ static void setup_impdiff(Ctx &ctx) {
         s.sy = b.g.sy; s.sz = b.g.sz;
       }
       ctx.usolver[c][par].reset(new MGSolver);
-      ctx.usolver[c][par]->setup(ctx, std::move(sb), false, 1);
+      ctx.usolver[c][par]->setup(ctx, std::move(sb), false, 1, (c == 0 ? AK_U0 : (c == 1 ? AK_V0 : AK_W0)) + par);
     }
   for (int is = 0; is < ctx.prm.nscal; ++is) {
     std::vector<SBox> sb(nl);
@@ -320,7 +319,7 @@ static void setup_impdiff(Ctx &ctx) {
       s.sy = b.g.sy; s.sz = b.g.sz;
     }
     ctx.ssolver[is].reset(new MGSolver);
-    ctx.ssolver[is]->setup(ctx, std::move(sb), false, 1);
+    ctx.ssolver[is]->setup(ctx, std::move(sb), false, 1, AK_S0 + is);
   }
 }
 
@@ -338,12 +337,13 @@ static void commit(Ctx &ctx) {
   q_range(ctx, ctx.nq, ctx.comm.me, ctx.q0, ctx.q1);
   if (batched && ctx.q1 <= ctx.q0) throw Error("more processes than wavenumbers: nothing to solve on this process");
   if (ctx.comm.nproc > 1) {
-    if (!batched) throw Error("a 3-D solve (fft_axis = 0) distributed over several processes is not available in this build");
     size_t bytes = 0;
     for (auto &bp : ctx.boxes) {
       bytes += (size_t)(8 + ctx.prm.nscal) * (bp->g.alloc_elems() * sizeof(double) + 256);
       bytes += (size_t)2 * (8 + ctx.prm.nscal) * ((size_t)(bp->g.n[1] + 2) * (bp->g.n[2] + 2) * sizeof(double) + 256);   // x-face landing buffers
     }
+    if (!batched)   // 3-D solve: the iterate of every multigrid level lives in the arena (coarse levels sum to < 1 level 0)
+      for (auto &bp : ctx.boxes) bytes += (size_t)(2.2 * (bp->g.alloc_elems() * sizeof(double))) + 32 * 256;
     for (BlockInfo &B : blocks) {
       int pd[2], q = 0;
       for (int d = 0; d < 3; ++d) if (d != fa) pd[q++] = d;
@@ -376,7 +376,7 @@ static void commit(Ctx &ctx) {
     alloc_field(ctx, b.p, b.g, r, AK_P);
     b.rhs.alloc(b.g);
     b.pp_is_po = !batched;
-    if (b.pp_is_po) b.po.alloc(b.g);
+    if (b.pp_is_po) alloc_field(ctx, b.po, b.g, r, AK_PO);
     else { alloc_field(ctx, b.pp, b.g, r, AK_PP); b.stage.alloc(b.g); }
     b.du.alloc(b.g); b.dv.alloc(b.g); b.dw.alloc(b.g);
     for (int s = 0; s < ctx.prm.nscal; ++s) { alloc_field(ctx, b.s[s], b.g, r, AK_S0 + s); b.ds[s].alloc(b.g); }
@@ -391,7 +391,7 @@ static void commit(Ctx &ctx) {
                mom_tma_make_map(b.tmap_hist[1], b.dv.p, b.g, true) && mom_tma_make_map(b.tmap_hist[2], b.dw.p, b.g, true);
     if (ctx.comm.nproc > 1) {   // landing buffers of the x-faces pushed by neighbours on other processes (bound.cu)
       std::vector<int> fkeys = {AK_U0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P};
-      if (!b.pp_is_po) fkeys.push_back(AK_PP);
+      fkeys.push_back(b.pp_is_po ? AK_PO : AK_PP);
       for (int s = 0; s < ctx.prm.nscal; ++s) fkeys.push_back(AK_S0 + s);
       for (int ib = 0; ib < 2; ++ib) {
         const int nbr = b.info.nb[0][ib];
@@ -498,7 +498,7 @@ static void commit(Ctx &ctx) {
     if (ctx.prm.plane_solver == 2 && tdir < 0)
       throw Error("plane_solver = direct: the 2-D problems are not separable (planes split over blocks, or no uniform "
                   "periodic/Neumann/Dirichlet direction); use the multigrid");
-    S.setup(ctx, std::move(sb), batched, tdir >= 0 ? 1 : 24);
+    S.setup(ctx, std::move(sb), batched, tdir >= 0 ? 1 : 24, batched ? -1 : AK_PO);
     if (tdir >= 0) { S.direct.setup(ctx, S, tdir); ctx.direct_on = true; }
   }
   if (ctx.prm.impdiff) setup_impdiff(ctx);
@@ -514,6 +514,12 @@ static void commit(Ctx &ctx) {
 static void finish_setup(Ctx &ctx) {
   const int nl = (int)ctx.boxes.size();
   const int fa = ctx.prm.fft_axis - 1;
+  ctx.psolver.connect(ctx);
+  for (int c = 0; c < 3; ++c)
+    for (int par = 0; par < 2; ++par)
+      if (ctx.usolver[c][par]) ctx.usolver[c][par]->connect(ctx);
+  for (int is = 0; is < SNAC_MAX_SCAL; ++is)
+    if (ctx.ssolver[is]) ctx.ssolver[is]->connect(ctx);
   for (int par = 0; par < 2; ++par) {
     std::vector<ExField> ef;
     for (int f = 0; f < 3; ++f)
@@ -538,7 +544,7 @@ static void finish_setup(Ctx &ctx) {
       ep.push_back(ExField{lb, b.p.p, b.g});
       epp.push_back(ExField{lb, b.pp_ptr(), b.g});
     }
-    const std::vector<int> kp = {AK_P}, kpp = {AK_PP};
+    const std::vector<int> kp = {AK_P}, kpp = {ctx.boxes[0]->pp_is_po ? AK_PO : AK_PP};
     ctx.ex_p.build(ctx, ep, nullptr, &kp);
     ctx.ex_pp.build(ctx, epp, nullptr, &kpp);
     auto cbc = [](Box &b, int, int d, int ib) -> char { return b.info.cbcpre[d][ib]; };
@@ -826,8 +832,34 @@ __global__ void publish_kernel(const double *vals, double *const *slots, int n, 
   __threadfence_system();   // performed at the peers before the kernel completes (the flag is written by a later kernel)
 }
 
-// local reductions, then the MPI_ALLREDUCEs of chkdt/chkdiv (src/chkdt.f90:48, src/chkdiv.f90:42-43):
-// every process writes its three partial results into every peer's arena and reduces on the host
+// MPI_ALLREDUCE of up to 3 values that sit in device memory: every process writes them into its slot of every peer's
+// reduction table (double-buffered by the parity of the sequence number), one handshake, and the table is read back
+void Ctx::peer_reduce(const double *d_vals, int n, double *sum, double *mx) {
+  if (n < 1 || n > 3) throw Error("peer_reduce: 1 to 3 values");
+  const int np = comm.nproc;
+  if (np == 1) {
+    SNAC_CUDA(cudaMemcpyAsync(h_red, d_vals, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    SNAC_CUDA(cudaStreamSynchronize(stream));
+    for (int q = 0; q < n; ++q) { sum[q] = h_red[q]; mx[q] = h_red[q]; }
+    return;
+  }
+  if (!ready) throw Error("snac_comm_connect has not been called");
+  const size_t base = PeerComm::FLAGS_BYTES + (size_t)((comm.seq[CH_REDUCE] + 1) & 1) * MAXPROC * 4 * sizeof(double);
+  std::vector<double *> slots(np);
+  for (int p = 0; p < np; ++p) slots[p] = reinterpret_cast<double *>(comm.peer[p] + base) + 4 * comm.me;
+  SNAC_CUDA(cudaMemcpyAsync(d_slots, slots.data(), np * sizeof(double *), cudaMemcpyHostToDevice, stream));
+  publish_kernel<<<1, 32, 0, stream>>>(d_vals, d_slots, n, np);
+  launches++;
+  comm.handshake(*this, CH_REDUCE, ~0u);
+  SNAC_CUDA(cudaMemcpyAsync(h_red, comm.arena + base, 4 * MAXPROC * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  SNAC_CUDA(cudaStreamSynchronize(stream));
+  check_peers(*this);
+  for (int q = 0; q < n; ++q) { sum[q] = 0.0; mx[q] = -1e300; }
+  for (int p = 0; p < np; ++p)
+    for (int q = 0; q < n; ++q) { sum[q] += h_red[4 * p + q]; mx[q] = std::max(mx[q], h_red[4 * p + q]); }
+}
+
+// local reductions, then the MPI_ALLREDUCEs of chkdt/chkdiv (src/chkdt.f90:48, src/chkdiv.f90:42-43)
 static void do_chk(Ctx &ctx, bool want_dt, double *out3) {
   SNAC_CUDA(cudaMemsetAsync(ctx.red.raw, 0, 8 * sizeof(double), ctx.stream));
   {
@@ -835,31 +867,9 @@ static void do_chk(Ctx &ctx, bool want_dt, double *out3) {
     for (auto &b : ctx.boxes) launch_chk(ctx, *b, ctx.red.raw);
   }
   (void)want_dt;
-  const int np = ctx.comm.nproc;
-  if (np == 1) {
-    SNAC_CUDA(cudaMemcpyAsync(ctx.h_red, ctx.red.raw, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-    SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
-    for (int q = 0; q < 3; ++q) out3[q] = ctx.h_red[q];
-    return;
-  }
-  if (!ctx.ready) throw Error("snac_comm_connect has not been called");
-  // slot of process `me` in the reduction table of every arena (double-buffered by parity of the sequence)
-  const size_t base = PeerComm::FLAGS_BYTES + (size_t)((ctx.comm.seq[CH_REDUCE] + 1) & 1) * MAXPROC * 4 * sizeof(double);
-  std::vector<double *> slots(np);
-  for (int p = 0; p < np; ++p) slots[p] = reinterpret_cast<double *>(ctx.comm.peer[p] + base) + 4 * ctx.comm.me;
-  SNAC_CUDA(cudaMemcpyAsync(ctx.d_slots, slots.data(), np * sizeof(double *), cudaMemcpyHostToDevice, ctx.stream));
-  publish_kernel<<<1, 32, 0, ctx.stream>>>(ctx.red.raw, ctx.d_slots, 3, np);
-  ctx.launches++;
-  ctx.comm.handshake(ctx, CH_REDUCE, ~0u);
-  SNAC_CUDA(cudaMemcpyAsync(ctx.h_red, ctx.comm.arena + base, 4 * MAXPROC * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-  SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
-  check_peers(ctx);
-  out3[0] = 0.0; out3[1] = 0.0; out3[2] = 0.0;
-  for (int p = 0; p < np; ++p) {
-    out3[0] = std::max(out3[0], ctx.h_red[4 * p + 0]);
-    out3[1] += ctx.h_red[4 * p + 1];
-    out3[2] = std::max(out3[2], ctx.h_red[4 * p + 2]);
-  }
+  double sum[3], mx[3];
+  ctx.peer_reduce(ctx.red.raw, 3, sum, mx);
+  out3[0] = mx[0]; out3[1] = sum[1]; out3[2] = mx[2];
 }
 
 static const double RKC[3][2] = {{32.0 / 60.0, 0.0}, {25.0 / 60.0, -17.0 / 60.0}, {45.0 / 60.0, -25.0 / 60.0}};
@@ -875,11 +885,10 @@ static void do_rk_scal(Ctx &ctx, int irk, double dt, int is) {
   if (forced) SNAC_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), ctx.stream));
   for (auto &b : ctx.boxes) launch_scal_update(ctx, *b, is, f1, f2, f12, d_sum);
   double f = 0.0;
-  if (forced) {   // bulk_mean_s (src/scal.f90:156-179)
-    if (ctx.comm.nproc > 1) throw Error("forced scalars on several processes are not available in this build");
-    SNAC_CUDA(cudaMemcpyAsync(ctx.h_red, d_sum, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
-    SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
-    f = ctx.prm.scalf[is] - ctx.h_red[0] / ctx.prm.vol_all;
+  if (forced) {   // bulk_mean_s (src/scal.f90:156-179; MPI_ALLREDUCE :177)
+    double sum[3], mx[3];
+    ctx.peer_reduce(d_sum, 1, sum, mx);
+    f = ctx.prm.scalf[is] - sum[0] / ctx.prm.vol_all;
   }
   if (ctx.prm.impdiff || forced)
     for (auto &b : ctx.boxes) launch_scal_finish(ctx, *b, is, f12, f);

@@ -80,7 +80,7 @@ void launch_face_ops(Ctx &ctx, const DevOps<FaceOp> &ops) {
 }
 
 void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::vector<NbTable> *nbs, const std::vector<int> *keys,
-                     bool ids_local) {
+                     bool ids_local, const std::vector<Grid3> *rank_grids, bool stage_x) {
   // `fields` holds, for each exchanged array, one entry per local box, grouped: fields[f*nl + lb].
   // Neighbour on this GPU: the ghost plane of box lb on side ib is pulled from the neighbour's
   // first/last interior plane (src/bound.f90:602-607).  Neighbour owned by another process: this
@@ -117,7 +117,7 @@ void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::ve
             if (!keys || ctx.comm.nproc == 1) throw Error("halo exchange with a box owned by another process needs snac_comm_connect");
             const int proc = ctx.owner[nbr];
             const snac_box &w = ctx.world[nbr];
-            const Grid3 rg = Grid3::make(w.hi[0] - w.lo[0] + 1, w.hi[1] - w.lo[1] + 1, w.hi[2] - w.lo[2] + 1);
+            const Grid3 rg = rank_grids ? (*rank_grids)[nbr] : Grid3::make(w.hi[0] - w.lo[0] + 1, w.hi[1] - w.lo[1] + 1, w.hi[2] - w.lo[2] + 1);
             if (rg.n[da] != me.g.n[da] || rg.n[db] != me.g.n[db])
               throw Error("halo exchange: neighbouring boxes are not face-congruent");
             const long sidx = (ib == 0) ? 1 : me.g.n[d];            // my lo / hi interior plane
@@ -125,7 +125,7 @@ void Exchange::build(Ctx &ctx, const std::vector<ExField> &fields, const std::ve
             op.ssa = me.g.st(da); op.ssb = me.g.st(db);
             op.src = me.p + sidx * me.g.st(d);
             static const bool xstage = !(getenv("SNAC_XFACE_STAGE") && atoi(getenv("SNAC_XFACE_STAGE")) == 0);
-            if (d == 0 && xstage) {
+            if (d == 0 && xstage && stage_x) {
               // An x-face is one element per row: pushed in place it is (n2+2)(n3+2) separate 8-byte stores
               // over NVLink.  It is gathered into a dense landing buffer of the neighbour instead (coalesced
               // remote stores); the neighbour scatters it into its ghost column once the push has arrived.

@@ -179,8 +179,11 @@ struct Exchange {
   unsigned mask[3] = {0, 0, 0};   // peer processes this exchange pushes to / receives from, per direction
   int key0 = -1;                  // arena key of the first exchanged array (remote neighbours), -1: local only
   // nbs == nullptr: the boxes' physical neighbour tables
+  // rank_grids: the layout of the exchanged arrays on EVERY box of the run (multigrid levels, shortened staggered
+  // ranges); default: Grid3::make of the box.  stage_x: x-faces of remote neighbours go through landing buffers.
   void build(Ctx &ctx, const std::vector<ExField> &fields, const std::vector<NbTable> *nbs = nullptr,
-             const std::vector<int> *keys = nullptr, bool ids_local = false);
+             const std::vector<int> *keys = nullptr, bool ids_local = false, const std::vector<Grid3> *rank_grids = nullptr,
+             bool stage_x = true);
   void run(Ctx &ctx, int dir) const;      // one direction
   void run_all(Ctx &ctx) const;           // x, then y, then z (edges/corners propagate)
 };
@@ -354,6 +357,13 @@ struct MGSolver {
   DevBuf norms;                    // [2*nq]: sum r^2, sum b^2 per plane
   std::vector<double> h_norms;
   bool ids_local = false;          // neighbour ids of the solver boxes are solver-box indices (batched: blocks)
+  // several processes, boxes coupled across them (3-D solves, Helmholtz solves of IMPDIFF): the level arrays live in
+  // the arena, the halo tables are built once the peers are mapped (connect), residual norms are summed over the
+  // processes (every process takes the same decisions: the handshake sequences stay aligned)
+  bool distributed = false;
+  int key0 = -1;                   // arena key of the level-0 iterate
+  std::vector<std::vector<Grid3>> rank_grids;   // [level][rank]: layout of that level's arrays on every box of the run
+  void connect(Ctx &ctx);
   bool plane_local = false;        // fused shared-memory path (planes not split over boxes)
   int first_smem_level = 0;        // first level handled by the one-CTA-per-plane kernel
   bool coarse_single = false;      // that kernel computes in FP32 (only ever a coarse-grid correction, never level 0)
@@ -377,7 +387,7 @@ struct MGSolver {
   int default_sweeps = 2;          // smoothing sweeps per leg when snac_params does not say: V(2,2) converges at ~0.13 per
                                    // cycle on isotropic grids (V(1,1): 0.27) and stays convergent on stretched / anisotropic ones
   double guess_scale = 1.0;        // factor applied to the initial guess (the previous solution) by the first cycle
-  void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched, int max_levels = 24);
+  void setup(Ctx &ctx, std::vector<SBox> &&boxes, bool batched, int max_levels = 24, int key0 = -1);
   void solve(Ctx &ctx);
   const Grid3 &grid0(int lb) const { return levels[0]->boxes[lb].g; }
   // Plane-local path: four arrays can hold the level-0 iterate of a box -- the current one, the ping-pong
@@ -441,6 +451,8 @@ enum CommChannel : int { CH_READY = 0, CH_ARRIVED = 1, CH_FFT = 2, CH_SOLVED = 3
 enum ArenaKey : int {   // exported arrays: per box (rank) or per block
   AK_U0 = 0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P, AK_PP, AK_S0 /* .. AK_S0+7 */, AK_SLAB_X = 24, AK_SLAB_B = 25,
   AK_SLAB_X1 = 26, AK_SLAB_K1 = 27, AK_SLAB_K2 = 28,  // the other arrays that can hold the solver's level-0 iterate (MGSolver::xslot)
+  AK_PO = 16,          // iterate of the 3-D pressure solve (fft_axis = 0)
+  AK_MGX = 32,         // + level: iterate of a coarse level of the 3-D pressure multigrid (levels 1 .. 23)
   AK_XSTAGE = 64   // + 2 * (key of the field) + side: dense landing buffer of an x-face pushed by the neighbour (bound.cu)
 };
 struct ArenaRec { int id, key; long long off; };   // id: box rank or block; off: bytes from the arena base
@@ -535,6 +547,8 @@ struct Ctx {
   double *h_red = nullptr;  // pinned
   double **d_slots = nullptr;
   Box &box_of_rank(int rank);
+  // sum / max over the processes of up to 3 device values each (peer tables + one handshake; api.cu)
+  void peer_reduce(const double *d_vals, int n, double *sum, double *mx);
 };
 
 struct ProfScope {

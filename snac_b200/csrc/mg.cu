@@ -275,10 +275,13 @@ static void build_dir(MGLevelBox &L, int d, bool coupled, const std::vector<doub
   L.tab[d].upload(tab);
 }
 
-void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max_levels) {
+void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max_levels, int key0_) {
   sboxes = std::move(boxes_);
   fft_dir = batched ? 2 : -1;
   ids_local = batched;
+  key0 = key0_;
+  distributed = !batched && ctx.comm.nproc > 1;
+  if (distributed && key0 < 0) throw Error("multigrid over several processes: the level-0 iterate must be a published array");
   const int nl = (int)sboxes.size();
   bool coupled[3];
   for (int d = 0; d < 3; ++d) coupled[d] = (d != fft_dir);
@@ -321,6 +324,24 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
       for (int d = 0; d < 3; ++d) build_dir(L, d, coupled[d], sb.d1[d], sb.d2[d], sb.sgn[d], sb.phys[d], sb.qqq[d]);
     }
   }
+  // distributed: the layout and the cell widths of EVERY box of the run, level by level (host arithmetic only: each
+  // process repeats the coarsening of its neighbours' boxes instead of exchanging ghost widths on the device)
+  std::vector<std::array<std::vector<double>, 3>> all_w;   // [rank][d]: widths 1..n of the current level (ghost entries unused)
+  if (distributed) {
+    const int nr = ctx.prm.nrank;
+    rank_grids.assign(1, std::vector<Grid3>(nr));
+    all_w.resize(nr);
+    for (int r = 0; r < nr; ++r) {
+      const snac_box &w = ctx.world[r];
+      Grid3 g = Grid3::make(w.hi[0] - w.lo[0] + 1, w.hi[1] - w.lo[1] + 1, w.hi[2] - w.lo[2] + 1);
+      for (int d = 0; d < 3; ++d) {
+        const bool stag = sboxes[0].qqq[d] != 0;   // the same for every box of a solver
+        all_w[r][d] = stag ? ctx.world_dc[d][r] : ctx.world_df[d][r];
+        if (stag && w.is_bound[d][1]) g.n[d] -= 1;   // the shortened staggered range keeps the strides of the box
+      }
+      rank_grids[0][r] = g;
+    }
+  }
   // coarser levels
   for (;;) {
     MGLevel &F = *levels.back();
@@ -335,6 +356,17 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
         for (int i = 1; i <= n; ++i) hsum[d] += F.boxes[lb].h_w[d][i];
         ncnt[d] += n;
       }
+    if (distributed) {   // the same decision on every process: statistics over all boxes of the run
+      for (int d = 0; d < 3; ++d) { hsum[d] = 0.0; ncnt[d] = 0; all_one[d] = true; }
+      const std::vector<Grid3> &RG = rank_grids.back();
+      for (size_t r = 0; r < RG.size(); ++r)
+        for (int d = 0; d < 3; ++d) {
+          const int n = RG[r].n[d];
+          if (n != 1) all_one[d] = false;
+          for (int i = 1; i <= n; ++i) hsum[d] += all_w[r][d][i];
+          ncnt[d] += n;
+        }
+    }
     double hmin = 1e300;
     for (int d = 0; d < 3; ++d)
       if (coupled[d] && !all_one[d]) hmin = std::min(hmin, hsum[d] / ncnt[d]);
@@ -355,7 +387,9 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
       MGLevelBox &c = C.boxes[lb];
       c.g = Grid3::make(co[0] ? (f.g.n[0] + 1) / 2 : f.g.n[0], co[1] ? (f.g.n[1] + 1) / 2 : f.g.n[1],
                         co[2] ? (f.g.n[2] + 1) / 2 : f.g.n[2]);
-      c.x.alloc(c.g); c.b.alloc(c.g);
+      if (distributed) c.x.adopt(ctx.comm.alloc(c.g.alloc_elems(), ctx.boxes[lb]->info.rank, AK_MGX + (int)levels.size() - 1));
+      else c.x.alloc(c.g);
+      c.b.alloc(c.g);
       c.xp = c.x.p; c.bp = c.b.p;
       for (int d = 0; d < 3; ++d) {
         const int n = c.g.n[d];
@@ -367,6 +401,38 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
         c.h_w[d][n + 1] = c.h_w[d][n];
       }
     }
+    if (distributed) {
+      // coarse widths and layouts of every box of the run; ghost widths of the local boxes from their neighbours'
+      const std::vector<Grid3> &RF = rank_grids[rank_grids.size() - 1];
+      std::vector<Grid3> RC(RF.size());
+      std::vector<std::array<std::vector<double>, 3>> cw(RF.size());
+      for (size_t r = 0; r < RF.size(); ++r) {
+        RC[r] = Grid3::make(co[0] ? (RF[r].n[0] + 1) / 2 : RF[r].n[0], co[1] ? (RF[r].n[1] + 1) / 2 : RF[r].n[1],
+                            co[2] ? (RF[r].n[2] + 1) / 2 : RF[r].n[2]);
+        for (int d = 0; d < 3; ++d) {
+          const int n = RC[r].n[d], nf = RF[r].n[d];
+          cw[r][d].assign(n + 2, 1.0);
+          for (int i = 1; i <= n; ++i)
+            cw[r][d][i] = co[d] ? all_w[r][d][2 * i - 1] + (2 * i <= nf ? all_w[r][d][2 * i] : 0.0) : all_w[r][d][i];
+        }
+      }
+      for (int lb = 0; lb < nl; ++lb) {
+        MGLevelBox &c = C.boxes[lb];
+        for (int d = 0; d < 3; ++d) {
+          if (!coupled[d]) continue;
+          const int n = c.g.n[d];
+          for (int ib = 0; ib < 2; ++ib) {
+            const int nbr = nbt[lb].nb[d][ib];
+            if (nbr < 0) continue;
+            c.h_w[d][ib == 0 ? 0 : n + 1] = ib == 0 ? cw[nbr][d][RC[nbr].n[d]] : cw[nbr][d][1];
+          }
+        }
+      }
+      all_w.swap(cw);
+      rank_grids.push_back(RC);
+      for (int lb = 0; lb < nl; ++lb)
+        SNAC_CUDA(cudaMemsetAsync(C.boxes[lb].x.p - 15, 0, C.boxes[lb].g.alloc_elems() * sizeof(double), ctx.stream));
+    } else
     // ghost widths across box interfaces: exchange a field that carries the width along d
     {
       std::vector<ExField> ef;
@@ -412,8 +478,8 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
       }
     }
   }
-  // halo exchange of x on level 0 (coarser ones were built above)
-  {
+  // halo exchange of x on level 0 (coarser ones were built above); several processes: once the peers are mapped
+  if (!distributed) {
     std::vector<ExField> ef;
     for (int lb = 0; lb < nl; ++lb) ef.push_back(ExField{lb, levels[0]->boxes[lb].xp, levels[0]->boxes[lb].g});
     levels[0]->ex.build(ctx, ef, &nbt, nullptr, ids_local);
@@ -488,6 +554,22 @@ void MGSolver::setup(Ctx &ctx, std::vector<SBox> &&boxes_, bool batched, int max
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
+// several processes: halo tables of every level, neighbours' arrays addressed through the mapped arenas
+void MGSolver::connect(Ctx &ctx) {
+  if (!distributed) return;
+  const int nl = (int)sboxes.size();
+  std::vector<NbTable> nbt(nl);
+  for (int lb = 0; lb < nl; ++lb)
+    for (int d = 0; d < 3; ++d)
+      for (int ib = 0; ib < 2; ++ib) nbt[lb].nb[d][ib] = (d != fft_dir) ? sboxes[lb].nb[d][ib] : -1;
+  for (size_t l = 0; l < levels.size(); ++l) {
+    std::vector<ExField> ef;
+    for (int lb = 0; lb < nl; ++lb) ef.push_back(ExField{lb, levels[l]->boxes[lb].xp, levels[l]->boxes[lb].g});
+    const std::vector<int> keys = {l == 0 ? key0 : AK_MGX + (int)l};
+    levels[l]->ex.build(ctx, ef, &nbt, &keys, false, &rank_grids[l], false);
+  }
+}
+
 namespace {
 struct Cycle {
   Ctx &ctx;
@@ -531,7 +613,7 @@ struct Cycle {
         for (int d = 0; d < 3; ++d) co[d] = F.coarsen[d];
         cg = c.g;
         cb = c.bp;
-        SNAC_CUDA(cudaMemsetAsync(c.x.buf.raw, 0, c.x.buf.elems * sizeof(double), ctx.stream));
+        SNAC_CUDA(cudaMemsetAsync(c.x.p - 15, 0, c.g.alloc_elems() * sizeof(double), ctx.stream));   // (owned or in the arena)
       }
       dim3 blk = mg_block(cg, S.fft_dir), grd = mg_grid(blk, cg.n[0], cg.n[1], cg.n[2]);
       mg_restrict_kernel<<<grd, blk, 0, ctx.stream>>>(B, cb, cg.sy, cg.sz, cg.n[0], cg.n[1], cg.n[2], co[0], co[1], co[2],
@@ -809,8 +891,19 @@ void MGSolver::solve(Ctx &ctx) {
     if (nlev == 1) cy.sweeps(0, cy.nbot, false);
     else cy.sweeps(0, cy.npre, false);
     cy.restrict_from(0, true, it == 0);
-    SNAC_CUDA(cudaMemcpyAsync(h_norms.data(), norms.raw, nn, cudaMemcpyDeviceToHost, ctx.stream));
-    SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+    if (distributed) {
+      // MPI_ALLREDUCE of the residual norms (HYPRE's stopping test is global): every process gets the same sums and
+      // takes the same decisions below; the sums go back to the device for mg_zero_planes_kernel
+      if (nq != 1) throw Error("multigrid over several processes: one system per solve expected");
+      double sum[3], mx[3];
+      ctx.peer_reduce(norms.raw, 2, sum, mx);
+      h_norms[0] = sum[0];
+      if (it == 0) h_norms[1] = sum[1];
+      SNAC_CUDA(cudaMemcpyAsync(norms.raw, h_norms.data(), nn, cudaMemcpyHostToDevice, ctx.stream));
+    } else {
+      SNAC_CUDA(cudaMemcpyAsync(h_norms.data(), norms.raw, nn, cudaMemcpyDeviceToHost, ctx.stream));
+      SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
     bool conv = true, any_zero = false;
     double worst = 0.0;
     for (int q = 0; q < nq; ++q) {

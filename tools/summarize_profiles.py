@@ -55,7 +55,7 @@ def launches(tag, src, cmd):
             f.write(f"| {k} | {n} | {t:.1f} | {t / total:.3f} |\n")
 
 
-def full(tag, rep, cmd, workload):
+def full(tag, rep, cmd, workload, points):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -98,8 +98,8 @@ def full(tag, rep, cmd, workload):
                         seen[cls] = b
         f.write("\nDRAM bytes per launch of the largest launch of each class (-> `ncu_traffic.json`): " +
                 ", ".join(f"{k} {v / 1e6:.1f} MB" for k, v in seen.items()) + "\n")
-    for k, v in seen.items():
-        traffic[f"{workload}:{k}"] = v
+    for k, v in seen.items():   # per grid point of the captured workload: bench.py scales it to the points of its launches
+        traffic[f"{workload}:{k}"] = {"dram_bytes_per_point": v / points, "captured_on_points": points, "capture": f"{tag}_ncu_full_summary.md"}
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 
 
@@ -110,8 +110,9 @@ if __name__ == "__main__":
     ap.add_argument("--full")
     ap.add_argument("--cmd", default="")
     ap.add_argument("--workload", default="channel")
+    ap.add_argument("--points", type=float, default=1.0, help="grid points a full-field launch of the captured run covers")
     a = ap.parse_args()
     if a.launches:
         launches(a.tag, a.launches, a.cmd)
     if a.full:
-        full(a.tag, a.full, a.cmd, a.workload)
+        full(a.tag, a.full, a.cmd, a.workload, a.points)
