@@ -221,9 +221,8 @@ static std::vector<BlockInfo> merge_blocks(Ctx &ctx, const std::vector<BlockInfo
 // Returns the first wavenumber q0 and the count (as q1 - q0); wavenumber k of the slab is
 // q0 + k * q_stride(ctx).
 static bool q_is_cyclic(const Ctx &ctx) {
-  static const bool off = getenv("SNAC_SLAB_CYCLIC") && atoi(getenv("SNAC_SLAB_CYCLIC")) == 0;
   const int np = ctx.comm.nproc;
-  return !off && np > 1 && (np & (np - 1)) == 0;
+  return np > 1 && (np & (np - 1)) == 0;
 }
 static int q_stride(const Ctx &ctx) { return q_is_cyclic(ctx) ? ctx.comm.nproc : 1; }
 static void q_range(const Ctx &ctx, int nq, int proc, int &q0, int &q1) {
@@ -934,14 +933,6 @@ static void substep(Ctx &ctx, int irk, double dt) {
     ProfScope ps(ctx, PC_FILLPS, pts);
     for (auto &b : ctx.boxes) launch_fillps_bc(ctx, *b, dtrk);
   }
-  // experiment: the correction pressure is the pressure change over the sub-step, proportional to its
-  // size to leading order, so the previous solution scaled by the ratio of the sub-step sizes could be
-  // a closer initial guess than the previous solution itself (plane-local solver path)
-  {
-    static const bool on = getenv("SNAC_GUESS_SCALE") && atoi(getenv("SNAC_GUESS_SCALE")) != 0;   // opt-in: measured slower on the TGV case (4.99 vs 4.56 cycles per solve)
-    ctx.psolver.guess_scale = (on && ctx.psolver.plane_local && ctx.prev_dtrk > 0.0) ? dtrk / ctx.prev_dtrk : 1.0;
-    ctx.prev_dtrk = dtrk;
-  }
   ctx.psolver.hist_key = irk - 1;   // the three pressure solves of a step behave differently, each like its predecessor a step earlier
   if (ctx.prm.fft_axis > 0) {
     do_fft(ctx, +1, fused_rhs ? dtrk : 0.0);
@@ -950,28 +941,20 @@ static void substep(Ctx &ctx, int irk, double dt) {
   } else {
     do_solve(ctx);
   }
-  ctx.psolver.guess_scale = 1.0;
   do_boundp(ctx, SNAC_FIELD_PP);
   {
     ProfScope ps(ctx, PC_CORREC, pts);
     for (auto &b : ctx.boxes) launch_correc_updt(ctx, *b, dtrk, alpha, true, true);
   }
   {   // bounduvw(.true.), inflow(.true.), boundp(p): the halos of u,v,w,p in one exchange, then the face fills
-    static const bool merged = !(getenv("SNAC_MERGE_HALO") && atoi(getenv("SNAC_MERGE_HALO")) == 0);
-    if (merged) {
-      {
-        ProfScope ps(ctx, PC_HALO_BC);
-        ctx.ex_uvwp[ctx.par].run_all(ctx);
-        ctx.bc_uvw[ctx.par][1].run(ctx);
-      }
-      do_inflow(ctx, true);    // src/main.f90:1028
+    {
       ProfScope ps(ctx, PC_HALO_BC);
-      ctx.bc_p.run(ctx);
-    } else {
-      do_bounduvw(ctx, true);
-      do_inflow(ctx, true);
-      do_boundp(ctx, SNAC_FIELD_P);
+      ctx.ex_uvwp[ctx.par].run_all(ctx);
+      ctx.bc_uvw[ctx.par][1].run(ctx);
     }
+    do_inflow(ctx, true);    // src/main.f90:1028
+    ProfScope ps(ctx, PC_HALO_BC);
+    ctx.bc_p.run(ctx);
   }
 }
 

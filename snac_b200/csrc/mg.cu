@@ -209,7 +209,6 @@ __global__ void mg_finalize_kernel(double *x0, const double *x1, long sy, long s
 // smoothing sweeps per leg of the V-cycle: snac_params, else SNAC_MG_NSWEEP, else the solver's default
 static void mg_sweeps(const Ctx &ctx, const MGSolver &S, int &npre, int &npost) {
   int def = S.default_sweeps;
-  if (const char *e = getenv("SNAC_MG_NSWEEP")) def = std::max(1, atoi(e));
   npre = ctx.prm.mg_npre > 0 ? ctx.prm.mg_npre : def;
   npost = ctx.prm.mg_npost > 0 ? ctx.prm.mg_npost : def;
 }
@@ -718,20 +717,7 @@ struct Cycle {
       a.nq = S.nq; a.want_b = want_b ? 1 : 0;
       a.npre = npre; a.npost = npost; a.nbot = nbot;
       a.npre_low = npre; a.npost_low = npost;
-      {
-        static const bool adapt = !(getenv("SNAC_MG_COARSE_ADAPT") && atoi(getenv("SNAC_MG_COARSE_ADAPT")) == 0);
-        a.adaptive = (ls > 0 && adapt) ? 1 : 0;
-      }
-      if (ls > 0) {   // tuning hooks for the FP32 coarse-grid correction: sweeps per leg, depth of the hierarchy
-        static const int csw = getenv("SNAC_MG_COARSE_NSW") ? atoi(getenv("SNAC_MG_COARSE_NSW")) : 0;
-        static const int cml = getenv("SNAC_MG_COARSE_MAXLEV") ? atoi(getenv("SNAC_MG_COARSE_MAXLEV")) : 0;
-        static const int cnb = getenv("SNAC_MG_COARSE_NBOT") ? atoi(getenv("SNAC_MG_COARSE_NBOT")) : 0;
-        if (csw > 0) a.npre = a.npost = a.npre_low = a.npost_low = csw;
-        static const int clo = getenv("SNAC_MG_COARSE_NSW_LOW") ? atoi(getenv("SNAC_MG_COARSE_NSW_LOW")) : 0;
-        if (clo > 0) a.npre_low = a.npost_low = clo;
-        if (cml > 0) a.nlev = std::min(a.nlev, cml);
-        if (cnb > 0) a.nbot = cnb;
-      }
+      a.adaptive = ls > 0 ? 1 : 0;
       a.active = S.d_active;
       launch_mg_coarse(ctx.stream, a, S.coarse_single);
       ctx.launches++;
@@ -754,11 +740,6 @@ void MGSolver::stats(Ctx &ctx, int *iters, double *relres, double *mean_iters) {
       last_mean_iters += it[q];
     }
     last_mean_iters /= nq;
-    if (getenv("SNAC_MG_DUMP")) {   // diagnostic: V-cycles per wavenumber
-      fprintf(stderr, "mg iters per plane:");
-      for (int q = 0; q < nq; ++q) fprintf(stderr, " %d", it[q]);
-      fprintf(stderr, "\n");
-    }
   }
   if (iters) *iters = last_iters;
   if (relres) *relres = last_relres;
@@ -777,11 +758,10 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
   ctx.launches++;
   int it = 0;
   // record of the last solve with the same key (see MGSolver::hist)
-  static const bool use_hist = !(getenv("SNAC_MG_HISTORY") && atoi(getenv("SNAC_MG_HISTORY")) == 0);
   const int key = S.hist_key & (MGSolver::HIST_KEYS - 1);
   const int *prev = S.hist(key, 1 - S.hist_cur[key]);
   int *cur = S.hist(key, S.hist_cur[key]);
-  const int prev_n = use_hist ? S.hist_n[key] : 0;
+  const int prev_n = S.hist_n[key];
   int polled = nq;
   auto predict = [&](int i) -> int {   // planes still iterating after cycle i
     if (i < 0) return nq;
@@ -789,8 +769,7 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
     return std::max(1, polled);
   };
   {   // initial guess: the last solution of this key (see MGSolver::xslot)
-    static const bool per_key = !(getenv("SNAC_MG_GUESS_PER_KEY") && atoi(getenv("SNAC_MG_GUESS_PER_KEY")) == 0);
-    if (per_key && in_alt && key != S.cur_key && S.slot_key[key] >= 0) {
+    if (in_alt && key != S.cur_key && S.slot_key[key] >= 0) {
       MGLevel &L0 = *S.levels[0];
       const int snew = S.slot_key[key];
       for (size_t lb = 0; lb < L0.boxes.size(); ++lb) {
@@ -852,8 +831,7 @@ static void solve_plane_local(Ctx &ctx, MGSolver &S, Cycle &cy) {
     // follows a down kernel): the buffers trade places and only planes with a zero right-hand side are
     // written (x = 0), instead of a copy of the whole solution (16 B per point per solve); the caller
     // re-points the transform at the new array, its own and its peers' (MGSolver::swapped, xslot).
-    static const bool no_swap = getenv("SNAC_MG_SWAP") && atoi(getenv("SNAC_MG_SWAP")) == 0;
-    const bool swap = in_alt && !no_swap;
+    const bool swap = in_alt;
     if (swap) std::swap(S.slot_primary, S.slot_scratch);
     for (size_t lb = 0; lb < L.boxes.size(); ++lb) {
       const Grid3 &g = L.boxes[lb].g;

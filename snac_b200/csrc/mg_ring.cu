@@ -489,10 +489,6 @@ __global__ void __launch_bounds__(WARPS_U * 32, SNAC_RING_MINB_U) mg_ring_up_ker
 // relatively more halo rows, long ones leave the last wave half empty.  The chunk height plus the
 // steps spent on its halos and on draining the pipeline is a multiple of the unroll period.
 static int ring_rows(int n1, int n2, int nact, int tx, int fixed, int period, int warps_per_cta, long slots) {
-  if (const char *e = getenv("SNAC_RING_MRY")) {
-    const int m = atoi(e);
-    if (m >= 2) return (m + 1) & ~1;
-  }
   const int ntx = (n1 + tx - 1) / tx;
   fixed = (fixed + 1) & ~1;            // steps of a chunk = mry + fixed: a multiple of the (even) period, mry even
   const int smin = 2 * period, smax = 264 / period * period;

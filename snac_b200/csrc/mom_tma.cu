@@ -265,9 +265,7 @@ bool launch_rk_mom_tma(Ctx &ctx, Box &b, int irk, double dt) {
   a.visc = ctx.prm.visc;
   // chunks along z: enough CTAs for a few waves of the device, chunks no shorter than 16 planes
   const int tiles = ((b.g.n[0] + TX - 1) / TX) * ((b.g.n[1] + TY - 1) / TY);
-  static const int kz_env = getenv("SNAC_MOM_KZ") ? atoi(getenv("SNAC_MOM_KZ")) : 0;
   int nchunk = std::max(1, std::min(b.g.n[2] / 16, (8 * 296 + tiles - 1) / tiles));
-  if (kz_env > 0) nchunk = std::max(1, (b.g.n[2] + kz_env - 1) / kz_env);
   a.kz = (b.g.n[2] + nchunk - 1) / nchunk;
   nchunk = (b.g.n[2] + a.kz - 1) / a.kz;
   dim3 blk(TX, TY, 1), grd((b.g.n[0] + TX - 1) / TX, (b.g.n[1] + TY - 1) / TY, nchunk);
