@@ -388,6 +388,7 @@ static void commit(Ctx &ctx) {
     }
     b.tma_ok = b.tma_ok && mom_tma_make_map(b.tmap[0][3], b.p.p, b.g) && mom_tma_make_map(b.tmap_hist[0], b.du.p, b.g, true) &&
                mom_tma_make_map(b.tmap_hist[1], b.dv.p, b.g, true) && mom_tma_make_map(b.tmap_hist[2], b.dw.p, b.g, true);
+    b.tma_pois_ok = b.tma_ok && pois_tma_setup(b);
     if (ctx.comm.nproc > 1) {   // landing buffers of the x-faces pushed by neighbours on other processes (bound.cu)
       std::vector<int> fkeys = {AK_U0, AK_U1, AK_V0, AK_V1, AK_W0, AK_W1, AK_P};
       fkeys.push_back(b.pp_is_po ? AK_PO : AK_PP);

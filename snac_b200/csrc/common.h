@@ -436,6 +436,12 @@ struct Box {
   alignas(64) unsigned char tmap[2][4][128];
   alignas(64) unsigned char tmap_hist[3][128];   // du, dv, dw (interior tiles)
   bool tma_ok = false;
+  // ... and for the z-marching fillps / correc kernels (pois_tma.cu): per velocity buffer the tiles of u and v with
+  // the column i-1 / the row j-1, the interior tiles of u,v,w ([0][3]: p), the tiles with halo of pp
+  alignas(64) unsigned char tmap_fill[2][2][128];
+  alignas(64) unsigned char tmap_int[2][4][128];
+  alignas(64) unsigned char tmap_pp[128];
+  bool tma_pois_ok = false;
   bool pp_is_po = false;    // 3-D solve: pp aliases the solver iterate
   double *pp_ptr() const { return pp_is_po ? po.p : pp.p; }
   BoxGeom geom() const;
@@ -573,6 +579,9 @@ struct ProfScope {
 void launch_rk_mom(Ctx &ctx, Box &b, int irk, double dt);
 bool launch_rk_mom_tma(Ctx &ctx, Box &b, int irk, double dt);   // mom_tma.cu; false: not applicable, use launch_rk_mom
 bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g, bool interior = false);
+bool pois_tma_setup(Box &b);                                     // pois_tma.cu
+bool launch_fillps_tma(Ctx &ctx, Box &b, double dtrk, bool do_bc);   // false: not applicable, use fillps_kernel
+bool launch_correc_tma(Ctx &ctx, Box &b, double dtrk, double alpha, bool do_correc, bool do_updt);
 void launch_fillps(Ctx &ctx, Box &b, double dtrk);
 void launch_fillps_bc(Ctx &ctx, Box &b, double dtrk);
 void launch_updt_rhs(Ctx &ctx, Box &b);

@@ -489,8 +489,8 @@ void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const do
   }
   if (pl.fast && !a.in_lane_t && !a.out_lane_t && !staged_only) {
     a.tab = pl.twiddle.p();
-    a.tp = radix::TP;
-    const long nt16 = (long)((n3[a.pd] + radix::TP - 1) / radix::TP) * n3[a.od];
+    a.tp = radix::tp_of(a.nt);
+    const long nt16 = (long)((n3[a.pd] + a.tp - 1) / a.tp) * n3[a.od];
     if (radix_launch(ctx.stream, a, dir, nt16)) {
       ctx.launches++;
       SNAC_CUDA(cudaGetLastError());

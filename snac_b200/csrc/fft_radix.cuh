@@ -139,10 +139,14 @@ SNAC_HD void dft(Cx (&v)[R]) {
   }
 }
 
-#ifndef SNAC_FFT_TP
-#define SNAC_FFT_TP 32
+// pencils per tile = lanes along the unit-stride direction.  32 pencils (rows of 256 bytes) up to n = 256; at n = 512 a
+// tile of 32 pencils fills 128 KB of shared memory: one CTA per SM, whose load, butterfly and store phases then run one
+// after the other with nothing to overlap them.  16 pencils (64 KB, two to three CTAs per SM) measured on the channel
+// (n = 512 along y, 1024 x 512 pencils): forward 4.28 -> 5.05 TB/s, backward 3.83 -> 4.88 TB/s.
+#ifndef SNAC_FFT_TP_LONG
+#define SNAC_FFT_TP_LONG 16
 #endif
-constexpr int TP = SNAC_FFT_TP;   // pencils per tile = lanes along the unit-stride direction (measured 8 / 16 / 32: 2.9 / 3.3 / 3.4 TB/s)
+__host__ __device__ constexpr int tp_of(int n) { return n >= 512 ? SNAC_FFT_TP_LONG : 32; }
 
 // per-thread constants of a tile
 struct Thread {
@@ -154,6 +158,7 @@ struct Thread {
 
 SNAC_HD Thread thread_of(const R2RArgs &a, int tid, int nthr, int tile) {
   Thread T;
+  const int TP = a.tp;
   T.p = tid % TP; T.jt = tid / TP; T.tpp = nthr / TP;
   const int ntp = (a.n[a.pd] + TP - 1) / TP;
   const int tpi = tile % ntp, o = tile / ntp;
@@ -182,6 +187,7 @@ struct Plan {
   static constexpr int M = R1 * R2;       // complex length
   static constexpr int N = 2 * M;         // real length
   static constexpr int S1 = R2;           // stride of the first pass = length of the contiguous runs
+  static constexpr int TP = tp_of(N);              // pencils per tile
   static constexpr int TPP = R1 < R2 ? R1 : R2;   // threads per pencil
   static constexpr int THREADS = TP * TPP;
   static constexpr size_t SMEM = (size_t)M * TP * sizeof(double2);
@@ -260,7 +266,7 @@ SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
 #pragma unroll
     for (int q = 0; q < R1; ++q) {
       const Cx y = q == 0 ? v[0] : cmul(v[q], tw_m(tw, j * q, P::M));
-      Z[(j + q * P::S1) * TP + T.p] = make_double2(y.x, y.y);
+      Z[(j + q * P::S1) * P::TP + T.p] = make_double2(y.x, y.y);
     }
   }
 }
@@ -277,7 +283,7 @@ SNAC_HD void run_pass(const R2RArgs &a, double2 *Z, const Thread &T) {   // radi
     Cx v[R2];
 #pragma unroll
     for (int r = 0; r < R2; ++r) {
-      const double2 z = Z[(q * P::S1 + r) * TP + T.p];
+      const double2 z = Z[(q * P::S1 + r) * P::TP + T.p];
       v[r] = Cx{z.x, z.y};
     }
     dft<R2, INV>(v);
@@ -289,7 +295,7 @@ SNAC_HD void run_pass(const R2RArgs &a, double2 *Z, const Thread &T) {   // radi
         w.y = -w.y;
         y = cmul(y, w);
       }
-      Z[(q * P::S1 + s) * TP + T.p] = make_double2(y.x, y.y);
+      Z[(q * P::S1 + s) * P::TP + T.p] = make_double2(y.x, y.y);
     }
   }
 }
@@ -308,7 +314,7 @@ SNAC_HD void fwd_untangle(const R2RArgs &a, const double2 *Z, const Thread &T) {
   for (int k0 = 0; k0 < nk; k0 += P::TPP) {
     const int k = k0 + T.jt;
     if (k >= nk) break;
-    const double2 zk2 = Z[P::loc(k) * TP + T.p], zm2 = Z[P::loc((m - k) & (m - 1)) * TP + T.p];
+    const double2 zk2 = Z[P::loc(k) * P::TP + T.p], zm2 = Z[P::loc((m - k) & (m - 1)) * P::TP + T.p];
     const Cx zk{zk2.x, zk2.y}, zm{zm2.x, zm2.y};
     const Cx e{0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y)};
     const Cx o{0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x)};   // -i/2 (zk - conj zm)
@@ -345,45 +351,62 @@ SNAC_HD void fwd_untangle(const R2RArgs &a, const double2 *Z, const Thread &T) {
 }
 
 // ---- backward --------------------------------------------------------------------------------
+// All the loads of a thread (four per wavenumber pair it untangles) are issued before the first of them is used:
+// issued pair by pair in front of the shared-memory stores, a thread had four loads in flight and the n = 512
+// transform (one CTA of 512 threads per SM) ran at 0.45 of the copy rate.
 template <int R1, int R2, bool SPLIT>
 SNAC_HD void bwd_tangle(const R2RArgs &a, double2 *Z, const Thread &T) {
   using P = Plan<R1, R2>;
   if (!T.valid) return;
   constexpr int m = P::M, n = P::N, nk = m / 2 + 1;
+  constexpr int NIT = (nk + P::TPP - 1) / P::TPP;
   const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
   const long isa = a.ist[a.axis], ib = T.ib;
   const double *wn = a.tab + 2 * (m / 2);
   const double *wd = wn + 2 * (m / 2 + 1);
-#pragma unroll
-  for (int k0 = 0; k0 < nk; k0 += P::TPP) {
-    const int k = k0 + T.jt;
-    if (k >= nk) break;
 #define SNAC_IN_AT(idx) R2R_IN_ATS(idx, ib, isa)
+  double in[NIT][4];   // per pair: the two halfcomplex (or DCT/DST) entries of X[k], then those of X[m-k]
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int k = it * P::TPP + T.jt;
+    in[it][0] = in[it][1] = in[it][2] = in[it][3] = 0.0;
+    if (k >= nk) continue;
+    const int kb = m - k;
+    if (!makhoul) {
+      in[it][0] = SNAC_IN_AT(k);
+      if (k > 0) in[it][1] = SNAC_IN_AT(n - k);
+      in[it][2] = SNAC_IN_AT(kb);
+      if (kb < m) in[it][3] = SNAC_IN_AT(n - kb);
+    } else {
+      in[it][0] = SNAC_IN_AT(sine ? (n - 1 - k) : k);
+      if (k > 0) in[it][1] = SNAC_IN_AT(sine ? (k - 1) : (n - k));
+      in[it][2] = SNAC_IN_AT(sine ? (n - 1 - kb) : kb);
+      if (kb > 0) in[it][3] = SNAC_IN_AT(sine ? (kb - 1) : (n - kb));
+    }
+  }
+#undef SNAC_IN_AT
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int k = it * P::TPP + T.jt;
+    if (k >= nk) continue;
     const int kb = m - k;
     Cx xk, xm;  // X[k], X[m-k]
     if (!makhoul) {
-      xk.x = SNAC_IN_AT(k);  xk.y = (k > 0) ? SNAC_IN_AT(n - k) : 0.0;
-      xm.x = SNAC_IN_AT(kb); xm.y = (kb < m) ? SNAC_IN_AT(n - kb) : 0.0;
+      xk = Cx{in[it][0], in[it][1]};
+      xm = Cx{in[it][2], in[it][3]};
     } else {
-      auto getx = [&](int kk) -> Cx {
-        const double c = SNAC_LDG(wd + 2 * kk), s_ = -SNAC_LDG(wd + 2 * kk + 1);
-        const int i0 = sine ? (n - 1 - kk) : kk;
-        const double a0 = SNAC_IN_AT(i0);
-        double a1 = 0.0;
-        if (kk > 0) { const int i1 = sine ? (kk - 1) : (n - kk); a1 = SNAC_IN_AT(i1); }
-        return Cx{c * a0 + s_ * a1, s_ * a0 - c * a1};
-      };
-      xk = getx(k);
-      xm = getx(kb);
+      const double c0 = SNAC_LDG(wd + 2 * k), s0 = -SNAC_LDG(wd + 2 * k + 1);
+      const double c1 = SNAC_LDG(wd + 2 * kb), s1 = -SNAC_LDG(wd + 2 * kb + 1);
+      xk = Cx{c0 * in[it][0] + s0 * in[it][1], s0 * in[it][0] - c0 * in[it][1]};
+      xm = Cx{c1 * in[it][2] + s1 * in[it][3], s1 * in[it][2] - c1 * in[it][3]};
     }
-#undef SNAC_IN_AT
     // Z[k] = (X[k] + conj X[m-k]) + i e^{+2 pi i k/n} (X[k] - conj X[m-k])
     const Cx w{SNAC_LDG(wn + 2 * k), -SNAC_LDG(wn + 2 * k + 1)};
     const Cx sum{xk.x + xm.x, xk.y - xm.y}, dif{xk.x - xm.x, xk.y + xm.y};
     const Cx wd_ = cmul(w, dif);
-    Z[P::loc(k & (m - 1)) * TP + T.p] = make_double2(sum.x - wd_.y, sum.y + wd_.x);
+    Z[P::loc(k & (m - 1)) * P::TP + T.p] = make_double2(sum.x - wd_.y, sum.y + wd_.x);
     if (k > 0 && k != kb)   // Z[m-k] = conj( (X[k] + conj X[m-k]) - i e^{+2 pi i k/n}(X[k] - conj X[m-k]) )
-      Z[P::loc(kb) * TP + T.p] = make_double2(sum.x + wd_.y, -(sum.y - wd_.x));
+      Z[P::loc(kb) * P::TP + T.p] = make_double2(sum.x + wd_.y, -(sum.y - wd_.x));
   }
 }
 
@@ -400,7 +423,7 @@ SNAC_HD void bwd_pass2(const R2RArgs &a, const double2 *Z, const Thread &T) {   
     Cx v[R1];
 #pragma unroll
     for (int q = 0; q < R1; ++q) {
-      const double2 z = Z[(q * P::S1 + j) * TP + T.p];
+      const double2 z = Z[(q * P::S1 + j) * P::TP + T.p];
       v[q] = Cx{z.x, z.y};
     }
     dft<R1, true>(v);

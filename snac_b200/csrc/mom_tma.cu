@@ -12,9 +12,7 @@
 // step ahead).  Global traffic is the algorithmic 7 reads + 6 writes per cell plus the halo of the tiles, which
 // neighbouring CTAs find in L2; the latency of the 25 stencil loads per cell, which bound the one-thread-per-cell
 // kernel (long-scoreboard stalls at 28 warps per SM), is paid once per plane by the TMA unit instead.
-#include <cuda.h>
-
-#include "common.h"
+#include "tma.cuh"
 
 namespace snac {
 
@@ -52,27 +50,11 @@ struct MomTmaArgs {
   int kz;              // planes per chunk
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "MBAR_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra MBAR_DONE;\n"
-      "bra MBAR_WAIT;\n"
-      "MBAR_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
+using tma::mbar_init;
+using tma::mbar_expect_tx;
+using tma::mbar_wait;
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  tma::load_3d(dst, map, bar, c0, c1, c2);
 }
 
 template <bool IMPDIFF, bool FIRST>
@@ -92,8 +74,7 @@ __global__ void __launch_bounds__(TX * TY, SNAC_MOM_MINB) rk_mom_tma_kernel(cons
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the barriers are visible to the TMA unit
+    tma::fence_barrier_init();   // the barriers are visible to the TMA unit
   }
   __syncthreads();
   // planes k0-1 .. k1+1 are needed; plane p (numbered from k0-1 = 0) lives in slot p mod NS
@@ -227,23 +208,25 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
-// Tensor map of one ghosted field for the BX x BY x 1 tiles of rk_mom_tma_kernel (interior = false) or for the
-// TX x TY x 1 tiles of an RK-history array (interior = true: the map starts at element (1,0,0), which is 128-byte
-// aligned; coordinates = (i-1, j, k)).  The map starts one
-// element before the (0,0,0) corner: that address is 16-byte aligned (Field3: the corner sits 15 doubles into a
-// 256-byte aligned allocation), so element (i,j,k) has the coordinates (i+1, j, k) and boxes start at even
-// coordinates.
-bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g, bool interior) {
+// Tensor map of a ghosted field for boxes of bx x by x 1 doubles (tma.cuh: base one element before the (0,0,0) corner,
+// or at element (1,0,0) when interior; both 16-byte aligned: the corner sits 15 doubles into a 256-byte aligned
+// allocation, Field3).
+bool tma_make_map(void *out128, const double *corner, const Grid3 &g, int bx, int by, bool interior) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const cuuint64_t gdim[3] = {(cuuint64_t)g.sy, (cuuint64_t)(g.n[1] + 2), (cuuint64_t)(g.n[2] + 2)};
   const cuuint64_t gstr[2] = {(cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8};
-  const cuuint32_t box[3] = {(cuuint32_t)(interior ? TX : BX), (cuuint32_t)(interior ? TY : BY), 1}, estr[3] = {1, 1, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1}, estr[3] = {1, 1, 1};
   void *base = const_cast<double *>(corner) + (interior ? 1 : -1);
   if (reinterpret_cast<size_t>(base) & 15) return false;
   return fn(static_cast<CUtensorMap *>(out128), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// the BX x BY tiles with halo of rk_mom_tma_kernel (interior = false) or the TX x TY tiles of an RK-history array
+bool mom_tma_make_map(void *out128, const double *corner, const Grid3 &g, bool interior) {
+  return tma_make_map(out128, corner, g, interior ? TX : BX, interior ? TY : BY, interior);
 }
 
 // returns false when this box / configuration is left to rk_mom_kernel (buoyancy term, no tensor maps)

@@ -70,6 +70,7 @@ static dim3 grid_for(const dim3 &blk, int n0, int n1, int n2) {
 }
 
 static void fill_common(Ctx &ctx, Box &b, double dtrk, int do_fill, int do_bc) {
+  if (do_fill == 1 && launch_fillps_tma(ctx, b, dtrk, do_bc != 0)) return;
   PoisArgs a;
   a.g = b.geom();
   a.u = b.u[ctx.par].p; a.v = b.v[ctx.par].p; a.w = b.w[ctx.par].p;
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(256) correc_kernel(const CorrArgs a) {
 }
 
 void launch_correc_updt(Ctx &ctx, Box &b, double dtrk, double alpha, bool do_correc, bool do_updt) {
+  if (launch_correc_tma(ctx, b, dtrk, alpha, do_correc, do_updt)) return;
   CorrArgs a;
   a.g = b.geom();
   a.u = b.u[ctx.par].p; a.v = b.v[ctx.par].p; a.w = b.w[ctx.par].p;

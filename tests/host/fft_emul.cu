@@ -14,7 +14,7 @@ using namespace snac;
 template <int R1, int R2>
 static void emulate(const R2RArgs &a, int dir, long ntiles) {
   using P = radix::Plan<R1, R2>;
-  std::vector<double2> Z((size_t)P::M * radix::TP);
+  std::vector<double2> Z((size_t)P::M * P::TP);
   for (long tile = 0; tile < ntiles; ++tile) {
     for (auto &z : Z) z = make_double2(NAN, NAN);
     auto phase = [&](auto fn) {
@@ -77,7 +77,7 @@ int main() {
           // the split side is the spectral one: two "owners", each holding half of the wavenumbers
           // in its own array (here: the same layout, second half in spec2)
           for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = fwd ? pst[d] : sst[d]; a.ost[d] = fwd ? sst[d] : pst[d]; }
-          a.axis = axis; a.nt = n; a.tp = radix::TP; a.pd = pd; a.od = od; a.kind = kind;
+          a.axis = axis; a.nt = n; a.tp = radix::tp_of(n); a.pd = pd; a.od = od; a.kind = kind;
           a.in_lane_t = a.out_lane_t = 0; a.scale = 0.75; a.tab = tab.data(); a.chunk = chunk; a.fill.on = 0;
           a.ns_mask = ncyc ? ncyc - 1 : 0; a.ns_shift = ncyc == 4 ? 2 : (ncyc == 2 ? 1 : 0);
           std::vector<double> in((size_t)n3[0] * n3[1] * n3[2]);
@@ -107,7 +107,7 @@ int main() {
             a.in_split = ncyc ? 2 : (split > 1 ? 1 : 0);
             a.outp[0] = phys.data() + pint; a.out_split = 0;
           }
-          const long ntiles = (long)((n3[pd] + radix::TP - 1) / radix::TP) * n3[od];
+          const long ntiles = (long)((n3[pd] + radix::tp_of(n) - 1) / radix::tp_of(n)) * n3[od];
           if (!run(a, fwd ? +1 : -1, ntiles)) { printf("no kernel for n = %d\n", n); return 1; }
           // reference: dense matrix-vector product along the axis
           double err = 0.0, nrm = 0.0;
@@ -163,13 +163,13 @@ int main() {
         R2RArgs a;
         for (int p = 0; p < 16; ++p) { a.inp[p] = nullptr; a.outp[p] = nullptr; }
         for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = pst[d]; a.ost[d] = sst[d]; }
-        a.axis = axis; a.nt = n; a.tp = radix::TP; a.pd = pd; a.od = od; a.kind = kind;
+        a.axis = axis; a.nt = n; a.tp = radix::tp_of(n); a.pd = pd; a.od = od; a.kind = kind;
         a.in_lane_t = a.out_lane_t = 0; a.scale = 1.0; a.tab = tab.data(); a.chunk = n;
         a.in_split = a.out_split = 0; a.ns_mask = a.ns_shift = 0; a.outp[0] = spec.data();
         a.fill.on = 1; a.fill.rdt = rdt;
         a.fill.vel[0] = u.data() + pint; a.fill.vel[1] = v.data() + pint; a.fill.vel[2] = w.data() + pint;
         for (int d = 0; d < 3; ++d) { a.fill.wq[d] = wq[d].data(); a.fill.gq[d] = gq[d].data(); a.fill.cb[d][0] = cb[d][0]; a.fill.cb[d][1] = cb[d][1]; }
-        const long ntiles = (long)((n3[pd] + radix::TP - 1) / radix::TP) * n3[od];
+        const long ntiles = (long)((n3[pd] + radix::tp_of(n) - 1) / radix::tp_of(n)) * n3[od];
         if (!run(a, +1, ntiles)) return 1;
         auto rhs = [&](int i, int j, int k) {   // 1-based cell
           const long c = i + psy * j + psz * k;
