@@ -247,6 +247,12 @@ static void alloc_field(Ctx &ctx, Field3 &f, const Grid3 &g, int id, int key) {
 // so they are solved on a single level with red-black Gauss-Seidel sweeps; the shifted diagonal is a
 // kernel argument, so nothing is re-assembled when dt changes (the reference re-creates and
 // re-sets-up its HYPRE solver on every call, src/solve_helmholtz.f90:85-86,134-135).
+// With FFT_AXIS on, the reference reduces each of these problems along the transform axis as it does for the pressure
+// (solve_impdiff_field_fft, src/solve_helmholtz.f90:32-100: scale, updt_rhs, transform, one 2-D solve per wavenumber,
+// back); that is a second algorithm for the SAME linear system (the transform diagonalises the discrete operator of
+// that direction, src/fft.f90:96-189), so the 3-D Gauss-Seidel solve below serves both builds: for a diagonal shift of
+// 2/(nu dtrk) it contracts by orders of magnitude per sweep and moves 24 B per point and sweep, less than a
+// transform pair + plane solves would (80 B per point).  The pressure keeps its transform path.
 static double helm_bc_coef(const Box &b, int d, int ib, char c, double bc, bool centered, int nhi, const std::vector<double> &d1,
                            const std::vector<double> &d2, const int periods[3]) {
   if (!b.info.is_bound[d][ib] || periods[d] != 0) return 0.0;
@@ -261,7 +267,6 @@ static double helm_bc_coef(const Box &b, int d, int ib, char c, double bc, bool 
 }
 
 static void setup_impdiff(Ctx &ctx) {
-  if (ctx.prm.fft_axis > 0) throw Error("implicit diffusion together with FFT_AXIS is not available in this build");
   const int nl = (int)ctx.boxes.size();
   auto fold_sign = [](char c, bool centered) {
     if (c == 'N') return 1.0;

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
 template <int R1, int R2, bool FWD, bool FILL, bool SPLIT>
 __global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS) r2r_radix_kernel(const R2RArgs a) {
   extern __shared__ __align__(16) double2 Zs[];
-  const radix::Thread T = radix::thread_of(a, threadIdx.x, blockDim.x, blockIdx.x);
+  const radix::Thread T = radix::thread_of<radix::Plan<R1, R2>::TP>(a, threadIdx.x, blockDim.x, blockIdx.x);
   if (FWD) {
     radix::fwd_pass1<R1, R2, FILL, SPLIT>(a, Zs, T);
     __syncthreads();

@@ -156,9 +156,9 @@ struct Thread {
   long ib, ob;         // offsets of the pencil's first element in the input / output arrays
 };
 
+template <int TP>
 SNAC_HD Thread thread_of(const R2RArgs &a, int tid, int nthr, int tile) {
   Thread T;
-  const int TP = a.tp;
   T.p = tid % TP; T.jt = tid / TP; T.tpp = nthr / TP;
   const int ntp = (a.n[a.pd] + TP - 1) / TP;
   const int tpi = tile % ntp, o = tile / ntp;

@@ -33,6 +33,12 @@ constexpr int BUF = ((BX * BY * 8 + 127) / 128) * 128 / 8;   // doubles per fiel
 #ifndef SNAC_MOM_NS
 #define SNAC_MOM_NS 6
 #endif
+// planes per chunk of the z-march.  Short chunks keep the CTAs of a wave in step, so that the halo of a tile is still
+// in L2 when the neighbouring CTA asks for it: chunks of 256 planes (channel, 1024 x 512 x 512) let them drift apart and
+// every halo came from DRAM again (117 B per point, 4.9 TB/s); 27 planes: 5.8 TB/s (profiles/r02_analysis.md)
+#ifndef SNAC_MOM_KZ
+#define SNAC_MOM_KZ 24
+#endif
 constexpr int NS = SNAC_MOM_NS;           // ring slots: planes k and k+1 in use, NS - 2 in flight
 constexpr unsigned SLOT_BYTES = 4u * BX * BY * 8u;
 constexpr int HBUF = TX * TY;             // doubles per RK-history tile (interior only) and slot
@@ -246,9 +252,9 @@ bool launch_rk_mom_tma(Ctx &ctx, Box &b, int irk, double dt) {
   a.du = b.du.p; a.dv = b.dv.p; a.dw = b.dw.p;
   a.f1 = RK[irk - 1][0] * dt; a.f2 = RK[irk - 1][1] * dt; a.f12 = a.f1 + a.f2;
   a.visc = ctx.prm.visc;
-  // chunks along z: enough CTAs for a few waves of the device, chunks no shorter than 16 planes
   const int tiles = ((b.g.n[0] + TX - 1) / TX) * ((b.g.n[1] + TY - 1) / TY);
-  int nchunk = std::max(1, std::min(b.g.n[2] / 16, (8 * 296 + tiles - 1) / tiles));
+  // chunks of SNAC_MOM_KZ planes; shorter ones (down to 8 planes) when a small box would not fill the device otherwise
+  int nchunk = std::max(1, std::max(b.g.n[2] / SNAC_MOM_KZ, std::min(b.g.n[2] / 8, (296 + tiles - 1) / tiles)));
   a.kz = (b.g.n[2] + nchunk - 1) / nchunk;
   nchunk = (b.g.n[2] + a.kz - 1) / a.kz;
   dim3 blk(TX, TY, 1), grd((b.g.n[0] + TX - 1) / TX, (b.g.n[1] + TY - 1) / TY, nchunk);

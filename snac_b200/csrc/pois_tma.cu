@@ -27,8 +27,11 @@ constexpr int FUX = TX + 2;
 constexpr int FU = FUX * TY, FV = TX * (TY + 1), FW = TX * TY;
 constexpr int FSLOT = FU + FV + FW;      // doubles; every part is a multiple of 128 bytes
 static_assert((FU * 8) % 128 == 0 && (FV * 8) % 128 == 0 && (FW * 8) % 128 == 0, "TMA destinations are 128-byte aligned");
+#ifndef SNAC_POIS_KZ
+#define SNAC_POIS_KZ 16
+#endif
 #ifndef SNAC_FILL_NS
-#define SNAC_FILL_NS 8
+#define SNAC_FILL_NS 10
 #endif
 constexpr int FNS = SNAC_FILL_NS;
 
@@ -43,7 +46,7 @@ struct FillTmaArgs {
   int kz;              // planes per chunk
 };
 
-__global__ void __launch_bounds__(TX * TY, 4) fillps_tma_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
+__global__ void __launch_bounds__(TX * TY, 3) fillps_tma_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
                                                                 const __grid_constant__ CUtensorMap tm_w, const FillTmaArgs a) {
   extern __shared__ __align__(128) double ring[];   // [FNS][u | v | w]
   __shared__ unsigned long long full[FNS];
@@ -114,7 +117,7 @@ constexpr int BX = TX + 4, BY = TY + 2;
 constexpr int CPP = ((BX * BY * 8 + 127) / 128) * 128 / 8, CF = TX * TY;
 constexpr int CSLOT = CPP + 4 * CF;
 #ifndef SNAC_CORR_NS
-#define SNAC_CORR_NS 6
+#define SNAC_CORR_NS 8
 #endif
 constexpr int CNS = SNAC_CORR_NS;
 
@@ -140,7 +143,7 @@ __device__ __forceinline__ void correc_ghost_column(const CorrTmaArgs &a, const 
 }
 
 template <bool IMPDIFF>
-__global__ void __launch_bounds__(TX * TY, 3) correc_tma_kernel(const __grid_constant__ CUtensorMap tm_pp, const __grid_constant__ CUtensorMap tm_u,
+__global__ void __launch_bounds__(TX * TY, 2) correc_tma_kernel(const __grid_constant__ CUtensorMap tm_pp, const __grid_constant__ CUtensorMap tm_u,
                                                                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_w,
                                                                 const __grid_constant__ CUtensorMap tm_p, const CorrTmaArgs a) {
   extern __shared__ __align__(128) double ring[];   // [CNS][pp with halo | u | v | w | p]
@@ -225,9 +228,10 @@ __global__ void __launch_bounds__(TX * TY, 3) correc_tma_kernel(const __grid_con
   }
 }
 
-// chunks along z: enough CTAs for a few waves of the device, chunks no shorter than 16 planes
-int planes_per_chunk(int tiles, int nplanes, int ctas_per_wave, int &nchunk) {
-  nchunk = std::max(1, std::min(nplanes / 16, (16 * ctas_per_wave + tiles - 1) / tiles));
+// chunks along z: short, so that the CTAs of a wave stay in step and find the halos of their tiles in L2 (mom_tma.cu)
+// (shorter ones, down to 8 planes, when a small box would not fill the device otherwise)
+int planes_per_chunk(int tiles, int nplanes, int &nchunk) {
+  nchunk = std::max(1, std::max(nplanes / SNAC_POIS_KZ, std::min(nplanes / 8, (444 + tiles - 1) / tiles)));
   const int kz = (nplanes + nchunk - 1) / nchunk;
   nchunk = (nplanes + kz - 1) / kz;
   return kz;
@@ -262,7 +266,7 @@ bool launch_fillps_tma(Ctx &ctx, Box &b, double dtrk, bool do_bc) {
   a.do_bc = do_bc;
   const int ntx = (b.g.n[0] + TX - 1) / TX, nty = (b.g.n[1] + TY - 1) / TY;
   int nchunk;
-  a.kz = planes_per_chunk(ntx * nty, b.g.n[2], 4 * 148, nchunk);
+  a.kz = planes_per_chunk(ntx * nty, b.g.n[2], nchunk);
   const size_t smem = (size_t)FNS * FSLOT * sizeof(double);
   static bool attr = false;
   if (!attr) {
@@ -293,7 +297,7 @@ bool launch_correc_tma(Ctx &ctx, Box &b, double dtrk, double alpha, bool do_corr
   a.do_correc = do_correc; a.do_updt = do_updt;
   const int ntx = (b.g.n[0] + TX - 1) / TX, nty = (b.g.n[1] + 2 + TY - 1) / TY;
   int nchunk;
-  a.kz = planes_per_chunk(ntx * nty, b.g.n[2] + 2, 3 * 148, nchunk);
+  a.kz = planes_per_chunk(ntx * nty, b.g.n[2] + 2, nchunk);
   const size_t smem = (size_t)CNS * CSLOT * sizeof(double);
   const CUtensorMap *tpp = reinterpret_cast<const CUtensorMap *>(b.tmap_pp), *tu = reinterpret_cast<const CUtensorMap *>(b.tmap_int[q][0]);
   const CUtensorMap *tv = reinterpret_cast<const CUtensorMap *>(b.tmap_int[q][1]), *tw = reinterpret_cast<const CUtensorMap *>(b.tmap_int[q][2]);

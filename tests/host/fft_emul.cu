@@ -18,7 +18,7 @@ static void emulate(const R2RArgs &a, int dir, long ntiles) {
   for (long tile = 0; tile < ntiles; ++tile) {
     for (auto &z : Z) z = make_double2(NAN, NAN);
     auto phase = [&](auto fn) {
-      for (int tid = 0; tid < P::THREADS; ++tid) fn(radix::thread_of(a, tid, P::THREADS, (int)tile));
+      for (int tid = 0; tid < P::THREADS; ++tid) fn(radix::thread_of<P::TP>(a, tid, P::THREADS, (int)tile));
     };
     if (dir > 0) {
       if (a.fill.on) phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, true, true>(a, Z.data(), T); });

@@ -486,7 +486,14 @@ SCAL_CASES = [("dhc", 2, False, True, 20),    # the reference's own differential
               ("dhc", 0, False, True, 5),
               ("dhc", 0, True, True, 5),      # config 5: implicit diffusion + Boussinesq, 3-D Helmholtz and Poisson solves
               ("channel", 0, True, False, 3),
-              ("cavity", 0, True, False, 3)]
+              ("cavity", 0, True, False, 3),
+              # solve_impdiff_field_fft (src/solve_helmholtz.f90:32-100): implicit diffusion in an FFT_AXIS build
+              ("dhc", 2, True, True, 5),
+              ("channel", 2, True, False, 3),
+              ("channel", 1, True, False, 3),
+              # transform along the wall-normal direction: 'DD' velocity walls, staggered w (RODFT00 of length n-1 in the
+              # reference).  ('DN' is not a case: the reference's eigenvalues leave it undefined, src/fft.f90:151-189)
+              ("channel", 3, True, False, 3)]
 
 
 @pytest.mark.parametrize("kind,fa,impdiff,bouss,nstep", SCAL_CASES)
@@ -496,7 +503,8 @@ def test_scalar_boussinesq_impdiff_steps_match_oracle(tmp_path, kind, fa, impdif
     if kind == "dhc":
         case = setup_case(os.path.join(GOLDEN, "dhc"), fft_axis=fa, impdiff=impdiff, boussinesq=bouss)
     else:
-        case = cases.make(kind, str(tmp_path), fft_axis=fa, impdiff=impdiff, boussinesq=bouss)
+        kw = dict(dims=(2, 1, 1), gr_z=0.0) if (kind, fa) == ("channel", 3) else {}
+        case = cases.make(kind, str(tmp_path), fft_axis=fa, impdiff=impdiff, boussinesq=bouss, **kw)
     o, g = _pair_with_scalars(case, tol=1e-12, maxiter=200, noise=(kind == "channel"))
     o.init_bc(); g.init_bc()
     o.set_dt(); g.set_dt()
