@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsnacb200.so")
-SOURCES = ["api.cu", "mom.cu", "mom_tma.cu", "bound.cu", "pois.cu", "pois_tma.cu", "fft.cu", "mg.cu", "mg_ring.cu", "mg_coarse.cu", "direct.cu", "comm.cu", "scal.cu", "output.cu"]
+SOURCES = ["api.cu", "mom.cu", "mom_tma.cu", "bound.cu", "pois.cu", "pois_tma.cu", "fft.cu", "mg.cu", "mg_ring.cu", "mg_coarse.cu", "mg_coop.cu", "direct.cu", "comm.cu", "scal.cu", "output.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -344,8 +344,15 @@ struct DirectSolver {
 };
 int direct_pick(const std::vector<SBox> &sboxes, bool ids_local, const std::vector<int> &local_of_rank);
 
+struct MGCoopState;   // mg_coop.cu: the general path as one cooperative launch per solve
+MGCoopState *mg_coop_setup(Ctx &ctx, MGSolver &S, const bool coupled[3]);
+void mg_coop_solve(Ctx &ctx, MGSolver &S, MGCoopState *st, int npre, int npost, int nbot);
+void mg_coop_collect(Ctx &ctx, MGSolver &S, MGCoopState *st);
+
 struct MGSolver {
   DirectSolver direct;
+  MGCoopState *coop = nullptr;
+  bool coop_tried = false;
   int fft_dir = -1;                // uncoupled direction in solver order (2 when batched) or -1
   int perm[3] = {0, 1, 2};         // solver direction -> physical direction
   std::vector<Field3> x0, b0;      // owned level-0 arrays (batched layout)

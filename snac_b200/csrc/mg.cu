@@ -708,6 +708,7 @@ struct Cycle {
 }  // namespace
 
 void MGSolver::stats(Ctx &ctx, int *iters, double *relres, double *mean_iters) {
+  mg_coop_collect(ctx, *this, coop);
   if (plane_local && !direct.on) {
     std::vector<int> it(nq);
     std::vector<double> rel(nq);
@@ -836,7 +837,14 @@ void MGSolver::solve(Ctx &ctx) {
     solve_plane_local(ctx, *this, cy);
     return;
   }
-  // general multi-box path: the host reads the per-plane residual norms once per cycle
+  // general multi-box path.  Every coupled box on this process: one cooperative launch per solve (mg_coop.cu)
+  if (!coop_tried) { coop = mg_coop_setup(ctx, *this, cy.coupled); coop_tried = true; }
+  if (coop) {
+    ProfScope ps(ctx, PC_MG_SMOOTH0);
+    mg_coop_solve(ctx, *this, coop, cy.npre, cy.npost, cy.nbot);
+    return;
+  }
+  // boxes coupled across processes: one launch per box, colour and level; the host reads the residual norms once per cycle
   const int nlev = (int)levels.size();
   const double tol = ctx.prm.hypre_tol;
   const int maxiter = std::max(ctx.prm.hypre_maxiter, 1);

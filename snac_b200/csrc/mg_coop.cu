@@ -263,8 +263,9 @@ __global__ void __launch_bounds__(COOP_THREADS) mg_coop_kernel(const CoopArgs a)
 struct MGCoopState {
   CoopArgs args;
   DevOps<CoopBox> boxes;
+  DevBuf result;
   int grid = 0;
-  double *h_result = nullptr;   // pinned: what the last solve wrote to norms[2 nq ..]
+  double *h_result = nullptr;   // pinned copy of `result`
   bool pending = false;
 };
 
@@ -328,7 +329,8 @@ MGCoopState *mg_coop_setup(Ctx &ctx, MGSolver &S, const bool coupled[3]) {
   a.norms = S.norms.raw;
   a.nq = S.nq;
   a.fft_dir = S.fft_dir;
-  a.result = S.norms.raw + 2 * (size_t)S.nq;
+  st->result.alloc(2);
+  a.result = st->result.raw;
   // one warp per row of level 0 is as wide as the grid needs to be; all CTAs must be resident at once
   const long want = std::max(1L, (rows0 + COOP_WARPS - 1) / COOP_WARPS);
   st->grid = (int)std::min<long>(want, (long)sms * std::min(per_sm, 4));
