@@ -27,7 +27,7 @@ namespace snac {
 
 namespace {
 
-constexpr int COOP_THREADS = 256, COOP_WARPS = COOP_THREADS / 32;
+constexpr int COOP_THREADS = 512, COOP_WARPS = COOP_THREADS / 32;
 
 struct CoopLevel {
   int box0, nbox;            // this level's entries of CoopArgs::boxes
@@ -46,7 +46,7 @@ struct CoopBox {
 
 struct CoopArgs {
   CoopLevel lev[24];
-  int nlev;
+  int nlev, ltail;           // levels ltail .. nlev-1: few enough rows for one CTA (mg_coop_kernel)
   const CoopBox *boxes;
   double *norms;             // [nq] sum r^2, [nq] sum b^2
   int nq;
@@ -176,35 +176,64 @@ __device__ void coop_zero_planes(const CoopArgs &a, long gwarp, long nwarps, int
   }
 }
 
+// who works on a phase: the whole grid (phases end at a grid-wide barrier) or, on the coarse tail of the hierarchy,
+// one CTA (phases end at __syncthreads: a level of a few hundred cells is done before a grid barrier would return)
+struct Team { long tid, size, warp, nwarps; };
+
+template <bool GRID>
+struct Exec {
+  const CoopArgs &a;
+  cg::grid_group &grid;
+  Team T;
+  int lane;
+  __device__ __forceinline__ void sync() { if (GRID) grid.sync(); else __syncthreads(); }
+  __device__ void exchange(int l) {
+    if (a.lev[l].ncp[0] + a.lev[l].ncp[1] + a.lev[l].ncp[2] == 0) return;   // (the same on every thread)
+    coop_exchange(a, l, T.tid, T.size);
+    sync();
+  }
+  __device__ void sweeps(int l, int n, bool reverse) {
+    for (int s = 0; s < n; ++s)
+      for (int c = 0; c < 2; ++c) {
+        coop_smooth(a, l, reverse ? 1 - c : c, T.warp, T.nwarps, lane);
+        sync();
+        exchange(l);
+      }
+  }
+  __device__ void restrict_from(int l, bool norms, bool want_b) {
+    coop_restrict(a, l, norms, want_b, T.warp, T.nwarps, lane, T.tid, T.size);
+    sync();
+  }
+  // one level of the downward leg (the bottom sweeps on the last level) / of the upward leg
+  __device__ void down(int l) {
+    if (l == a.nlev - 1) { sweeps(l, a.nbot, false); return; }
+    sweeps(l, a.npre, false);
+    restrict_from(l, false, false);
+  }
+  __device__ void up(int l) {
+    coop_prolong(a, l, T.warp, T.nwarps, lane);
+    sync();
+    exchange(l);
+    sweeps(l, a.npost, true);
+  }
+};
+
 __global__ void __launch_bounds__(COOP_THREADS) mg_coop_kernel(const CoopArgs a) {
   cg::grid_group grid = cg::this_grid();
   const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gsize = (long)gridDim.x * blockDim.x;
-  const long gwarp = gtid >> 5, nwarps = gsize >> 5;
   const int lane = threadIdx.x & 31;
   __shared__ double s_w[COOP_WARPS];
   __shared__ int s_f[COOP_WARPS][2];
+  Exec<true> G{a, grid, Team{gtid, gsize, gtid >> 5, gsize >> 5}, lane};
+  Exec<false> B{a, grid, Team{threadIdx.x, blockDim.x, threadIdx.x >> 5, blockDim.x >> 5}, lane};
+  const int lt = a.ltail;   // levels lt .. nlev-1 are walked by CTA 0 alone (nlev: none)
 
-  auto exchange = [&](int l) {
-    if (a.lev[l].ncp[0] + a.lev[l].ncp[1] + a.lev[l].ncp[2] == 0) return;   // (the same on every thread)
-    coop_exchange(a, l, gtid, gsize);
-    grid.sync();
-  };
-  auto sweeps = [&](int l, int n, bool reverse) {
-    for (int s = 0; s < n; ++s)
-      for (int c = 0; c < 2; ++c) {
-        coop_smooth(a, l, reverse ? 1 - c : c, gwarp, nwarps, lane);
-        grid.sync();
-        exchange(l);
-      }
-  };
-
-  exchange(0);
+  G.exchange(0);
   int it = 0;
   double worst = 0.0;
   for (;; ++it) {
-    sweeps(0, a.nlev == 1 ? a.nbot : a.npre, false);
-    coop_restrict(a, 0, true, it == 0, gwarp, nwarps, lane, gtid, gsize);
-    grid.sync();
+    G.sweeps(0, a.nlev == 1 ? a.nbot : a.npre, false);
+    G.restrict_from(0, true, it == 0);
     // stopping rule (the same numbers, the same arithmetic on every CTA: every thread takes the same branch)
     double w = 0.0;
     int notconv = 0, anyzero = 0;
@@ -228,31 +257,25 @@ __global__ void __launch_bounds__(COOP_THREADS) mg_coop_kernel(const CoopArgs a)
     worst = w;
     const bool conv = !notconv;
     if (it == 0 && anyzero) {
-      coop_zero_planes(a, gwarp, nwarps, lane);
+      coop_zero_planes(a, G.T.warp, G.T.nwarps, lane);
       grid.sync();
-      exchange(0);
-      if (worst > 0.0) {   // the coarse right-hand side used the old iterate there
-        coop_restrict(a, 0, false, false, gwarp, nwarps, lane, gtid, gsize);
-        grid.sync();
-      }
+      G.exchange(0);
+      if (worst > 0.0) G.restrict_from(0, false, false);   // the coarse right-hand side used the old iterate there
     }
     if ((it > 0 && conv) || it >= a.maxiter || worst == 0.0 || (a.nlev == 1 && conv)) break;
     grid.sync();   // every CTA has read the norms: the sums of r^2 start from zero again
     if (blockIdx.x == 0)
       for (int q = threadIdx.x; q < a.nq; q += blockDim.x) a.norms[q] = 0.0;
     if (a.nlev > 1) {
-      for (int l = 1; l < a.nlev; ++l) {
-        if (l == a.nlev - 1) { sweeps(l, a.nbot, false); break; }
-        sweeps(l, a.npre, false);
-        coop_restrict(a, l, false, false, gwarp, nwarps, lane, gtid, gsize);
+      for (int l = 1; l < lt; ++l) G.down(l);
+      if (lt < a.nlev) {
+        if (blockIdx.x == 0) {
+          for (int l = lt; l < a.nlev; ++l) B.down(l);
+          for (int l = a.nlev - 2; l >= lt; --l) B.up(l);
+        }
         grid.sync();
       }
-      for (int l = a.nlev - 2; l >= 0; --l) {
-        coop_prolong(a, l, gwarp, nwarps, lane);
-        grid.sync();
-        exchange(l);
-        sweeps(l, a.npost, true);
-      }
+      for (int l = min(lt, a.nlev - 1) - 1; l >= 0; --l) G.up(l);
     }
   }
   if (gtid == 0) { a.result[0] = (double)it; a.result[1] = worst; }
@@ -324,6 +347,9 @@ MGCoopState *mg_coop_setup(Ctx &ctx, MGSolver &S, const bool coupled[3]) {
     }
     if (l == 0) rows0 = cl.rows;
   }
+  // the coarse tail: from the first level (below level 0) with at most four rows per warp of a CTA
+  a.ltail = a.nlev;
+  for (int l = a.nlev - 1; l >= 1 && a.lev[l].rows <= 4 * COOP_WARPS; --l) a.ltail = l;
   st->boxes.upload(hb);
   a.boxes = st->boxes.d;
   a.norms = S.norms.raw;
@@ -331,9 +357,10 @@ MGCoopState *mg_coop_setup(Ctx &ctx, MGSolver &S, const bool coupled[3]) {
   a.fft_dir = S.fft_dir;
   st->result.alloc(2);
   a.result = st->result.raw;
-  // one warp per row of level 0 is as wide as the grid needs to be; all CTAs must be resident at once
-  const long want = std::max(1L, (rows0 + COOP_WARPS - 1) / COOP_WARPS);
-  st->grid = (int)std::min<long>(want, (long)sms * std::min(per_sm, 4));
+  // the grid is no wider than level 0 needs (a grid-wide barrier costs more the more CTAs take part); all CTAs must be
+  // resident at once
+  const long want = std::max(1L, (rows0 + 2 * COOP_WARPS - 1) / (2 * COOP_WARPS));   // two rows of level 0 per warp
+  st->grid = (int)std::min<long>(want, (long)sms * std::min(per_sm, 2));
   SNAC_CUDA(cudaMallocHost(&st->h_result, 2 * sizeof(double)));
   st->h_result[0] = st->h_result[1] = 0.0;
   return st.release();
