@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
 
 // register-radix kernels (fft_radix.cuh): one CTA per tile of 32 pencils
 template <int R1, int R2, bool FWD, bool FILL, bool SPLIT>
-__global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS) r2r_radix_kernel(const R2RArgs a) {
+__global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS, FWD ? radix::Plan<R1, R2>::MINB_FWD : 0) r2r_radix_kernel(const R2RArgs a) {
   extern __shared__ __align__(16) double2 Zs[];
   const radix::Thread T = radix::thread_of<radix::Plan<R1, R2>::TP>(a, threadIdx.x, blockDim.x, blockIdx.x);
   if (FWD) {
@@ -381,7 +381,11 @@ __global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS) r2r_radix_kernel
     radix::run_pass<R1, R2, false>(a, Zs, T);
     __syncthreads();
     radix::fwd_untangle<R1, R2, SPLIT>(a, Zs, T);
-    if (SPLIT) __threadfence_system();   // the forward transform stores into the owners' slabs, possibly over NVLink
+    // the forward transform stores into the owners' slabs, possibly over NVLink: performed there before the kernel
+    // completes.  One system-scope fence per CTA after the barrier (fences are cumulative: the stores of every thread
+    // that arrived at the barrier are ordered before what thread 0 does next) instead of one per thread: 256 threads
+    // waiting for the fabric's acknowledgements kept the CTA's registers and shared memory busy
+    if (SPLIT) { __syncthreads(); if (threadIdx.x == 0) __threadfence_system(); }
   } else {
     radix::bwd_tangle<R1, R2, SPLIT>(a, Zs, T);
     __syncthreads();
