@@ -632,6 +632,7 @@ __global__ void permute_copy_kernel(double *dst, long d0, long d1, long d2, cons
 }
 
 static void transfer(Ctx &ctx, int rank, int field, double *host, bool up) {
+  if (up) ctx.vel_epoch++;
   Box &b = ctx.box_of_rank(rank);
   const int lb = ctx.local_of_rank[rank];
   const bool batched = ctx.prm.fft_axis > 0;
@@ -679,6 +680,7 @@ static void transfer(Ctx &ctx, int rank, int field, double *host, bool up) {
 
 // ---- pieces of the sub-step ------------------------------------------------------------------
 static void do_rk_mom(Ctx &ctx, int irk, double dt) {
+  ctx.vel_epoch++;
   if (irk < 1 || irk > 3) throw Error("rk_mom: irk must be 1, 2 or 3");
   double pts = 0.0;
   for (auto &b : ctx.boxes) pts += (double)b->g.n[0] * b->g.n[1] * b->g.n[2];
@@ -688,6 +690,7 @@ static void do_rk_mom(Ctx &ctx, int irk, double dt) {
   ctx.par = 1 - ctx.par;
 }
 static void do_bounduvw(Ctx &ctx, bool is_correc) {
+  ctx.vel_epoch++;
   ProfScope ps(ctx, PC_HALO_BC);
   ctx.ex_uvw[ctx.par].run_all(ctx);
   ctx.bc_uvw[ctx.par][is_correc ? 1 : 0].run(ctx);
@@ -725,6 +728,7 @@ static void build_inflow(Ctx &ctx) {
 }
 static void do_inflow(Ctx &ctx, bool is_correc) {
   if (!ctx.has_inflow) return;
+  ctx.vel_epoch++;
   ProfScope ps(ctx, PC_HALO_BC);
   if (ctx.inflow_dirty) build_inflow(ctx);
   ctx.bc_inflow[ctx.par][is_correc ? 1 : 0].run(ctx);
@@ -866,6 +870,10 @@ void Ctx::peer_reduce(const double *d_vals, int n, double *sum, double *mx) {
 
 // local reductions, then the MPI_ALLREDUCEs of chkdt/chkdiv (src/chkdt.f90:48, src/chkdiv.f90:42-43)
 static void do_chk(Ctx &ctx, bool want_dt, double *out3) {
+  if (ctx.chk_epoch == ctx.vel_epoch) {   // (the same decision on every process: they make the same calls)
+    for (int q = 0; q < 3; ++q) out3[q] = ctx.chk_out[q];
+    return;
+  }
   SNAC_CUDA(cudaMemsetAsync(ctx.red.raw, 0, 8 * sizeof(double), ctx.stream));
   {
     ProfScope ps(ctx, PC_CHK);
@@ -875,6 +883,8 @@ static void do_chk(Ctx &ctx, bool want_dt, double *out3) {
   double sum[3], mx[3];
   ctx.peer_reduce(ctx.red.raw, 3, sum, mx);
   out3[0] = mx[0]; out3[1] = sum[1]; out3[2] = mx[2];
+  for (int q = 0; q < 3; ++q) ctx.chk_out[q] = out3[q];
+  ctx.chk_epoch = ctx.vel_epoch;
 }
 
 static const double RKC[3][2] = {{32.0 / 60.0, 0.0}, {25.0 / 60.0, -17.0 / 60.0}, {45.0 / 60.0, -25.0 / 60.0}};
@@ -919,6 +929,7 @@ static void do_helmholtz(Ctx &ctx, MGSolver &S, int comp /* 0..2 velocity, -1-is
 }
 
 static void substep(Ctx &ctx, int irk, double dt) {
+  ctx.vel_epoch++;
   const double dtrk = (RKC[irk - 1][0] + RKC[irk - 1][1]) * dt;
   const double alpha = -ctx.prm.visc * dtrk / 2.0;
   if (!ctx.ready) throw Error("snac_comm_connect has not been called");
@@ -1124,6 +1135,7 @@ int snac_solve_helmholtz(snac_handle *h) {
   })
 }
 int snac_correc(snac_handle *h, double dtrk) {
+  if (h) h->ctx.vel_epoch++;
   SNAC_TRY(h, for (auto &b : h->ctx.boxes) launch_correc_updt(h->ctx, *b, dtrk, 0.0, true, false))
 }
 int snac_updt_pressure(snac_handle *h, double alpha) {

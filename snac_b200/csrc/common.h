@@ -534,6 +534,10 @@ struct Ctx {
   std::vector<std::array<int, 3>> blocks_lo;
   std::vector<int> blocks_id;               // solver box -> id under which its slabs are published (first member block)
   std::vector<FFTRoute> route;              // per local box
+  // chkdt and chkdiv are one pass over u,v,w (K7): the reductions of the last pass are kept until the velocity changes
+  // (the time loop calls chkdt and chkdiv back to back, src/main.f90:1048-1069)
+  long long vel_epoch = 0, chk_epoch = -1;
+  double chk_out[3] = {0, 0, 0};
   int par = 0;                              // which velocity buffer is current
   double prev_dtrk = 0.0;                   // sub-step size of the previous pressure solve (initial-guess scaling)
   long long launches = 0;

@@ -131,15 +131,23 @@ struct CorrTmaArgs {
   int kz;
 };
 
-// the ghost columns i = 0 and i = n+1 lie outside the 128-byte aligned interior tiles: a lane of the first / last tile
-// along x corrects them in global memory (src/correc.f90:23-47: the ranges include the ghost layers)
-__device__ __forceinline__ void correc_ghost_column(const CorrTmaArgs &a, const double *sc, const double *sn, int oo, int ii, int j, int k) {
-  if (!a.do_correc || j > a.n[1] + 1) return;
-  const long c = ii + a.sy * j + a.sz * k;
-  const double p0 = sc[oo];
-  if (ii <= a.n[0]) a.u[c] -= a.dtrk * (sc[oo + 1] - p0) * __ldg(a.rdc[0] + ii);
-  if (j <= a.n[1]) a.v[c] -= a.dtrk * (sc[oo + BX] - p0) * __ldg(a.rdc[1] + j);
-  if (k <= a.n[2]) a.w[c] -= a.dtrk * (sn[oo] - p0) * __ldg(a.rdc[2] + k);
+// The ghost columns i = 0 and (when n is a multiple of the tile width) i = n+1 lie outside the 128-byte aligned interior
+// tiles; the reference's ranges include them (src/correc.f90:23-47).  They are corrected by a kernel of their own, one
+// thread per ghost cell: done by a lane of the first / last tile inside the z-march, their global read-modify-writes
+// sat in the critical path of every plane step of those CTAs (a quarter of all CTAs on a 256^3 box: 4.4 instead of
+// 6 TB/s).  Same arithmetic; pp is only read, so the order of the two kernels does not matter.
+__global__ void __launch_bounds__(128) correc_ghost_columns_kernel(const CorrTmaArgs a, const double *pp, int both) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. n1+1
+  const int k = blockIdx.y;                              // 0 .. n2+1
+  if (j > a.n[1] + 1) return;
+  for (int side = 0; side <= both; ++side) {
+    const int i = side == 0 ? 0 : a.n[0] + 1;
+    const long c = i + a.sy * j + a.sz * k;
+    const double p0 = pp[c];
+    if (i <= a.n[0]) a.u[c] -= a.dtrk * (pp[c + 1] - p0) * __ldg(a.rdc[0] + i);
+    if (j <= a.n[1]) a.v[c] -= a.dtrk * (pp[c + a.sy] - p0) * __ldg(a.rdc[1] + j);
+    if (k <= a.n[2]) a.w[c] -= a.dtrk * (pp[c + a.sz] - p0) * __ldg(a.rdc[2] + k);
+  }
 }
 
 template <bool IMPDIFF>
@@ -188,8 +196,6 @@ __global__ void __launch_bounds__(TX * TY, 2) correc_tma_kernel(const __grid_con
   }
   const int o = (ty + 1) * BX + tx + 2, of = CPP + ty * TX + tx;
   const long c0 = ic + a.sy * jc;
-  const bool ghost_lo = blockIdx.x == 0 && tx == 0;
-  const bool ghost_hi = (n0 % TX) == 0 && blockIdx.x == gridDim.x - 1 && tx == TX - 1;
   const bool inxy = i >= 1 && i <= n0 && j >= 1 && j <= n1;
 
   mbar_wait(&full[0], 0);
@@ -222,8 +228,6 @@ __global__ void __launch_bounds__(TX * TY, 2) correc_tma_kernel(const __grid_con
         a.p[c] = val;
       }
     }
-    if (ghost_lo) correc_ghost_column(a, sc, sn, o - 1, 0, j, k);
-    if (ghost_hi) correc_ghost_column(a, sc, sn, o + 1, n0 + 1, j, k);
     pkm = p0; p0 = pkp;
   }
 }
@@ -313,6 +317,10 @@ bool launch_correc_tma(Ctx &ctx, Box &b, double dtrk, double alpha, bool do_corr
     correc_tma_kernel<false><<<grd, blk, smem, ctx.stream>>>(*tpp, *tu, *tv, *tw, *tp, a);
   }
   ctx.launches++;
+  if (do_correc) {
+    correc_ghost_columns_kernel<<<dim3((b.g.n[1] + 2 + 127) / 128, b.g.n[2] + 2), 128, 0, ctx.stream>>>(a, b.pp_ptr(), (b.g.n[0] % TX) == 0 ? 1 : 0);
+    ctx.launches++;
+  }
   SNAC_CUDA(cudaGetLastError());
   return true;
 }
