@@ -759,19 +759,7 @@ static void do_boundp(Ctx &ctx, int field) {
     ctx.bc_s[field - SNAC_FIELD_S0].run(ctx);
   } else throw Error("boundp: field must be P, PP or a scalar");
 }
-// can fillps + updt_rhs be evaluated inside the forward transform for every box of this process?
-static bool can_fuse_fillps(Ctx &ctx) {
-  if (ctx.prm.fft_axis == 0) return false;
-  for (int lb = 0; lb < (int)ctx.boxes.size(); ++lb) {
-    Box &b = *ctx.boxes[lb];
-    const long pst[3] = {1, b.g.sy, b.g.sz};
-    if (!r2r_can_fill(ctx.plan_p, b.g.n, pst, ctx.route[lb].st)) return false;
-  }
-  return true;
-}
-
-// dir = +1 with dtrk > 0: the right-hand side is evaluated from u,v,w in the load stage (K3a fused into K3b)
-static void do_fft(Ctx &ctx, int dir, double dtrk = 0.0) {
+static void do_fft(Ctx &ctx, int dir) {
   if (ctx.prm.fft_axis == 0) throw Error("fft: the handle was created with fft_axis = 0");
   if (!ctx.ready) throw Error("snac_comm_connect has not been called");
   double pts = 0.0;
@@ -784,22 +772,10 @@ static void do_fft(Ctx &ctx, int dir, double dtrk = 0.0) {
     const long pint = 1 + b.g.sy + b.g.sz;   // first interior element
     if (dir > 0) {        // physical right-hand side -> the owners' slabs
       const double *in[1] = {b.rhs.p + pint};
-      if (dtrk > 0.0) {
-        R2RFill f;
-        f.vel[0] = b.u[ctx.par].p + pint; f.vel[1] = b.v[ctx.par].p + pint; f.vel[2] = b.w[ctx.par].p + pint;
-        for (int d = 0; d < 3; ++d) {
-          f.wq[d] = b.wq[d].p(); f.gq[d] = b.gq[d].p();
-          f.cb[d][0] = b.cbp[d][0]; f.cb[d][1] = b.cbp[d][1];
-        }
-        f.rdt = 1.0 / dtrk;
-        f.on = 1;
-        r2r_execute(ctx, ctx.plan_p, +1, b.g.n, in, 1, pst, R.b, R.nsplit, R.st, R.chunk, 1.0, &f, R.cyclic);
-      } else {
-        r2r_execute(ctx, ctx.plan_p, +1, b.g.n, in, 1, pst, R.b, R.nsplit, R.st, R.chunk, 1.0, nullptr, R.cyclic);
-      }
+      r2r_execute(ctx, ctx.plan_p, +1, b.g.n, in, 1, pst, R.b, R.nsplit, R.st, R.chunk, 1.0, R.cyclic);
     } else {              // the owners' solution slabs -> physical pp, times normfft (src/main.f90:1017-1020)
       double *out[1] = {b.pp.p + pint};
-      r2r_execute(ctx, ctx.plan_p, -1, b.g.n, R.x, R.nsplit, R.st, out, 1, pst, R.chunk, ctx.plan_p.normfft, nullptr, R.cyclic);
+      r2r_execute(ctx, ctx.plan_p, -1, b.g.n, R.x, R.nsplit, R.st, out, 1, pst, R.chunk, ctx.plan_p.normfft, R.cyclic);
     }
   }
   // forward: every process must have received all pieces of its slabs before solving
@@ -945,14 +921,13 @@ static void substep(Ctx &ctx, int irk, double dt) {
   do_inflow(ctx, false);   // src/main.f90:999
   double pts = 0.0;
   for (auto &b : ctx.boxes) pts += (double)b->g.n[0] * b->g.n[1] * b->g.n[2];
-  const bool fused_rhs = can_fuse_fillps(ctx);   // fillps + updt_rhs inside the forward transform
-  if (!fused_rhs) {
+  {
     ProfScope ps(ctx, PC_FILLPS, pts);
     for (auto &b : ctx.boxes) launch_fillps_bc(ctx, *b, dtrk);
   }
   ctx.psolver.hist_key = irk - 1;   // the three pressure solves of a step behave differently, each like its predecessor a step earlier
   if (ctx.prm.fft_axis > 0) {
-    do_fft(ctx, +1, fused_rhs ? dtrk : 0.0);
+    do_fft(ctx, +1);
     do_solve(ctx);
     do_fft(ctx, -1);
   } else {

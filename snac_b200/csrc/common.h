@@ -235,11 +235,9 @@ std::vector<double> r2r_eigenvalues(int n, const char bc[2], bool centered);
 // in_split/out_split > 1: that side's transform axis is split into chunks of `chunk` indices, one
 // base pointer per chunk (the owning process' slab, possibly in a peer's memory); cyclic: index t of the axis
 // lives in piece t mod nsplit at position t div nsplit instead
-struct R2RFill;   // fft_radix.cuh: forward transform fused with fillps + updt_rhs
-bool r2r_can_fill(const R2RPlan &pl, const int n3[3], const long ist[3], const long ost[3]);
 void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *const *in, int in_split,
                  const long ist[3], double *const *out, int out_split, const long ost[3], int chunk, double scale,
-                 const R2RFill *fill = nullptr, bool cyclic = false);
+                 bool cyclic = false);
 
 // ------------------------------------------------------------------------------------------
 // multigrid (mg.cu)

@@ -371,12 +371,12 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
 }
 
 // register-radix kernels (fft_radix.cuh): one CTA per tile of 32 pencils
-template <int R1, int R2, bool FWD, bool FILL, bool SPLIT>
+template <int R1, int R2, bool FWD, bool SPLIT>
 __global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS, FWD ? radix::Plan<R1, R2>::MINB_FWD : 0) r2r_radix_kernel(const R2RArgs a) {
   extern __shared__ __align__(16) double2 Zs[];
   const radix::Thread T = radix::thread_of<radix::Plan<R1, R2>::TP>(a, threadIdx.x, blockDim.x, blockIdx.x);
   if (FWD) {
-    radix::fwd_pass1<R1, R2, FILL, SPLIT>(a, Zs, T);
+    radix::fwd_pass1<R1, R2, SPLIT>(a, Zs, T);
     __syncthreads();
     radix::run_pass<R1, R2, false>(a, Zs, T);
     __syncthreads();
@@ -395,26 +395,24 @@ __global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS, FWD ? radix::Pla
   }
 }
 
-template <int R1, int R2, bool FWD, bool FILL, bool SPLIT>
+template <int R1, int R2, bool FWD, bool SPLIT>
 static void radix_go1(cudaStream_t st, const R2RArgs &a, long ntiles) {
   using P = radix::Plan<R1, R2>;
   static bool attr = false;
   if (!attr && P::SMEM > 48 * 1024) {
-    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, FWD, FILL, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, FWD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
     attr = true;
   }
-  r2r_radix_kernel<R1, R2, FWD, FILL, SPLIT><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
+  r2r_radix_kernel<R1, R2, FWD, SPLIT><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
 }
 
 template <int R1, int R2>
 static void radix_go(cudaStream_t st, const R2RArgs &a, int dir, long ntiles) {
   const bool split = a.in_split != 0 || a.out_split != 0;
-  if (dir > 0 && a.fill.on) {
-    if (split) radix_go1<R1, R2, true, true, true>(st, a, ntiles); else radix_go1<R1, R2, true, true, false>(st, a, ntiles);
-  } else if (dir > 0) {
-    if (split) radix_go1<R1, R2, true, false, true>(st, a, ntiles); else radix_go1<R1, R2, true, false, false>(st, a, ntiles);
+  if (dir > 0) {
+    if (split) radix_go1<R1, R2, true, true>(st, a, ntiles); else radix_go1<R1, R2, true, false>(st, a, ntiles);
   } else {
-    if (split) radix_go1<R1, R2, false, false, true>(st, a, ntiles); else radix_go1<R1, R2, false, false, false>(st, a, ntiles);
+    if (split) radix_go1<R1, R2, false, true>(st, a, ntiles); else radix_go1<R1, R2, false, false>(st, a, ntiles);
   }
 }
 
@@ -430,29 +428,10 @@ static bool radix_launch(cudaStream_t st, const R2RArgs &a, int dir, long ntiles
   }
 }
 
-// can the forward transform of this box evaluate its input from u,v,w (r2r_execute with `fill`)?
-bool r2r_can_fill(const R2RPlan &pl, const int n3[3], const long ist[3], const long ost[3]) {
-  // Opt-in (SNAC_FFT_FUSE_FILLPS=1).  Measured on TGV-256: the fused kernel moves 32 instead of 48 B
-  // per point but needs 128 registers and six loads per element in the butterfly's load stage;
-  // 0.75 ms per step against 0.42 (fillps) + 0.24 (transform) unfused.  A version that stages the
-  // u,v,w tiles in shared memory first is the next thing to try.
-  static const bool off = (getenv("SNAC_FFT_STAGED") && atoi(getenv("SNAC_FFT_STAGED")) != 0) ||
-                          !(getenv("SNAC_FFT_FUSE_FILLPS") && atoi(getenv("SNAC_FFT_FUSE_FILLPS")) != 0);
-  const int n = pl.nt;
-  return !off && pl.fast && pl.axis != 0 && ist[pl.axis] != 1 && ost[pl.axis] != 1 && n3[pl.axis] == n &&
-         (n == 32 || n == 64 || n == 128 || n == 256 || n == 512);
-}
-
 void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const double *const *in, int in_split,
                  const long ist[3], double *const *out, int out_split, const long ost[3], int chunk, double scale,
-                 const R2RFill *fill, bool cyclic) {
+                 bool cyclic) {
   R2RArgs a;
-  a.fill.on = 0;
-  if (fill) {
-    if (dir <= 0 || !r2r_can_fill(pl, n3, ist, ost)) throw Error("r2r_execute: this transform cannot be fused with fillps");
-    a.fill = *fill;
-    a.fill.on = 1;
-  }
   for (int p = 0; p < 16; ++p) { a.inp[p] = nullptr; a.outp[p] = nullptr; }
   for (int p = 0; p < std::max(in_split, 1); ++p) a.inp[p] = in[p];
   for (int p = 0; p < std::max(out_split, 1); ++p) a.outp[p] = out[p];

@@ -26,18 +26,6 @@
 
 namespace snac {
 
-// Source of a forward transform fused with fillps + updt_rhs (K3a+K3b, src/fillps.f90:29-53,
-// src/bound.f90:543-585): the right-hand side is evaluated from u,v,w inside the load stage of the
-// transform instead of being written to and read back from an array (32 instead of 48 B per point).
-struct R2RFill {
-  const double *vel[3];   // u,v,w: element (1,1,1) of arrays with the strides ist[] of the transform's input
-  const double *wq[3];    // ghosted weights (index 1..n): cell width, or 1 along the transform axis
-  const double *gq[3];    // 1, or 1/width along the transform axis
-  double cb[3][2];        // boundary right-hand-side coefficient per face (0: none)
-  double rdt;
-  int on;
-};
-
 struct R2RArgs {
   // first interior element of the input / output array; when the wavenumber axis of that side is
   // split over processes (nsplit > 1), one base per owning process, chosen by index / chunk
@@ -55,7 +43,6 @@ struct R2RArgs {
   int in_lane_t, out_lane_t;  // consecutive lanes walk along the transform axis (it has stride 1)
   double scale;
   const double *tab; // twiddles (fast) or dense matrix (generic)
-  R2RFill fill;      // forward radix kernels only
 };
 
 // element t of a pencil whose first element is at offset `base` and whose axis stride is `st`.
@@ -205,54 +192,13 @@ SNAC_HD bool is_makhoul(int kind) { return kind == K_REDFT10 || kind == K_RODFT1
 SNAC_HD bool is_sine(int kind) { return kind == K_RODFT10 || kind == K_RODFT01; }
 
 // ---- forward ---------------------------------------------------------------------------------
-// per-thread constants of the fused right-hand side (the radix kernels gather pencils along x: pd = 0)
-struct FillThread {
-  double wx, g0, w_od, g_od;
-  double bx;              // boundary terms of the faces normal to x and to od, without the weight along the axis
-  double b_od;
-  bool az;                // the transform axis is z (else y)
-};
-SNAC_HD FillThread fill_thread(const R2RArgs &a, const Thread &T) {
-  const R2RFill &f = a.fill;
-  FillThread F;
-  const int i = T.ip + 1, jo = T.o + 1;
-  F.az = a.axis == 2;
-  F.wx = SNAC_LDG(f.wq[0] + i); F.g0 = SNAC_LDG(f.gq[0] + i);
-  F.w_od = SNAC_LDG(f.wq[a.od] + jo); F.g_od = SNAC_LDG(f.gq[a.od] + jo);
-  F.bx = (i == 1 ? f.cb[0][0] : 0.0) + (i == a.n[0] ? f.cb[0][1] : 0.0);
-  F.b_od = (jo == 1 ? f.cb[a.od][0] : 0.0) + (jo == a.n[a.od] ? f.cb[a.od][1] : 0.0);
-  return F;
-}
-// right-hand side at element t of the pencil (fillps_kernel of pois.cu, same expression)
-SNAC_HD double fill_value(const R2RArgs &a, const Thread &T, const FillThread &F, int t) {
-  const R2RFill &f = a.fill;
-  const long c = T.ib + t * a.ist[a.axis];
-  const double *u = f.vel[0] + c, *vo = f.vel[a.od] + c, *va = f.vel[a.axis] + c;
-  const double du = SNAC_LDG(u) - SNAC_LDG(u - a.ist[0]);
-  const double d_od = SNAC_LDG(vo) - SNAC_LDG(vo - a.ist[a.od]);
-  const double d_ax = SNAC_LDG(va) - SNAC_LDG(va - a.ist[a.axis]);
-  const double w_ax = SNAC_LDG(f.wq[a.axis] + t + 1), g_ax = SNAC_LDG(f.gq[a.axis] + t + 1);
-  const double dv = F.az ? d_od : d_ax, dw = F.az ? d_ax : d_od;
-  const double g1 = F.az ? F.g_od : g_ax, g2 = F.az ? g_ax : F.g_od;
-  const double wx = F.wx, wy = F.az ? F.w_od : w_ax, wz = F.az ? w_ax : F.w_od;
-  double val = (dw * g2 * wx * wy + dv * g1 * wx * wz + du * F.g0 * wy * wz) * f.rdt;
-  // updt_rhs: faces normal to x, to od and to the axis
-  const double b_ax = (t == 0 ? f.cb[a.axis][0] : 0.0) + (t == a.n[a.axis] - 1 ? f.cb[a.axis][1] : 0.0);
-  val += F.bx * wy * wz;
-  val += F.az ? F.b_od * wx * wz : F.b_od * wx * wy;
-  val += F.az ? b_ax * wx * wy : b_ax * wx * wz;
-  return val;
-}
-
-template <int R1, int R2, bool FILL, bool SPLIT>
+template <int R1, int R2, bool SPLIT>
 SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
   using P = Plan<R1, R2>;
   if (!T.valid) return;
   const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
   const long isa = a.ist[a.axis];
   const double *tw = a.tab;
-  FillThread FT;
-  if (FILL) FT = fill_thread(a, T);
 #pragma unroll
   for (int j0 = 0; j0 < P::S1; j0 += P::TPP) {
     const int j = j0 + T.jt;
@@ -262,9 +208,7 @@ SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
     for (int r = 0; r < R1; ++r) {
       const int e = j + r * P::S1;
       const int t0 = tof(2 * e, P::N, makhoul), t1 = tof(2 * e + 1, P::N, makhoul);
-      double x0, x1;
-      if (FILL) { x0 = fill_value(a, T, FT, t0); x1 = fill_value(a, T, FT, t1); }
-      else { x0 = R2R_IN_ATS(t0, T.ib, isa); x1 = R2R_IN_ATS(t1, T.ib, isa); }
+      double x0 = R2R_IN_ATS(t0, T.ib, isa), x1 = R2R_IN_ATS(t1, T.ib, isa);
       if (sine && (t0 & 1)) x0 = -x0;
       if (sine && (t1 & 1)) x1 = -x1;
       v[r] = Cx{x0, x1};

@@ -21,8 +21,7 @@ static void emulate(const R2RArgs &a, int dir, long ntiles) {
       for (int tid = 0; tid < P::THREADS; ++tid) fn(radix::thread_of<P::TP>(a, tid, P::THREADS, (int)tile));
     };
     if (dir > 0) {
-      if (a.fill.on) phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, true, true>(a, Z.data(), T); });
-      else phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, false, true>(a, Z.data(), T); });
+      phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, true>(a, Z.data(), T); });
       phase([&](const radix::Thread &T) { radix::run_pass<R1, R2, false>(a, Z.data(), T); });
       phase([&](const radix::Thread &T) { radix::fwd_untangle<R1, R2, true>(a, Z.data(), T); });
     } else {
@@ -78,7 +77,7 @@ int main() {
           // in its own array (here: the same layout, second half in spec2)
           for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = fwd ? pst[d] : sst[d]; a.ost[d] = fwd ? sst[d] : pst[d]; }
           a.axis = axis; a.nt = n; a.tp = radix::tp_of(n); a.pd = pd; a.od = od; a.kind = kind;
-          a.in_lane_t = a.out_lane_t = 0; a.scale = 0.75; a.tab = tab.data(); a.chunk = chunk; a.fill.on = 0;
+          a.in_lane_t = a.out_lane_t = 0; a.scale = 0.75; a.tab = tab.data(); a.chunk = chunk;
           a.ns_mask = ncyc ? ncyc - 1 : 0; a.ns_shift = ncyc == 4 ? 2 : (ncyc == 2 ? 1 : 0);
           std::vector<double> in((size_t)n3[0] * n3[1] * n3[2]);
           for (auto &v : in) v = U(rng);
@@ -133,79 +132,6 @@ int main() {
             return 1;
           }
         }
-  // forward transform fused with fillps + updt_rhs: the right-hand side evaluated from u,v,w in the load
-  // stage (reference src/fillps.f90:29-53, src/bound.f90:543-585) against transform(dense) of the same
-  // right-hand side evaluated here with the expression of fillps_kernel (pois.cu)
-  for (int n : {32, 256})
-    for (int axis : {1, 2})
-      for (int kind : {K_R2HC, K_REDFT10, K_RODFT10}) {
-        int n3[3] = {37, 3, 3};
-        n3[axis] = n;
-        const int pd = 0, od = 3 - axis - pd;
-        const long psy = 48, psz = psy * (n3[1] + 2);
-        const long pst[3] = {1, psy, psz};
-        long sst[3];
-        sst[pd] = 1; sst[od] = 40; sst[axis] = 40L * n3[od];
-        const size_t pe = (size_t)psz * (n3[2] + 2) + 64, se = (size_t)sst[axis] * n + 64;
-        std::vector<double> u(pe), v(pe), w(pe), spec(se, 0.0);
-        for (auto *arr : {&u, &v, &w}) for (auto &x : *arr) x = U(rng);
-        std::vector<double> wq[3], gq[3];
-        double cb[3][2];
-        for (int d = 0; d < 3; ++d) {
-          wq[d].resize(n3[d] + 2); gq[d].resize(n3[d] + 2);
-          for (int i = 0; i < n3[d] + 2; ++i) { wq[d][i] = d == axis ? 1.0 : 0.5 + 0.3 * U(rng); gq[d][i] = d == axis ? 1.3 : 1.0; }
-          cb[d][0] = U(rng); cb[d][1] = U(rng);
-        }
-        const long pint = 1 + psy + psz;
-        const double rdt = 3.7;
-        const std::vector<double> tab = r2r_fast_tables(n);
-        const std::vector<double> Mx = dense_matrix(kind, n);
-        R2RArgs a;
-        for (int p = 0; p < 16; ++p) { a.inp[p] = nullptr; a.outp[p] = nullptr; }
-        for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = pst[d]; a.ost[d] = sst[d]; }
-        a.axis = axis; a.nt = n; a.tp = radix::tp_of(n); a.pd = pd; a.od = od; a.kind = kind;
-        a.in_lane_t = a.out_lane_t = 0; a.scale = 1.0; a.tab = tab.data(); a.chunk = n;
-        a.in_split = a.out_split = 0; a.ns_mask = a.ns_shift = 0; a.outp[0] = spec.data();
-        a.fill.on = 1; a.fill.rdt = rdt;
-        a.fill.vel[0] = u.data() + pint; a.fill.vel[1] = v.data() + pint; a.fill.vel[2] = w.data() + pint;
-        for (int d = 0; d < 3; ++d) { a.fill.wq[d] = wq[d].data(); a.fill.gq[d] = gq[d].data(); a.fill.cb[d][0] = cb[d][0]; a.fill.cb[d][1] = cb[d][1]; }
-        const long ntiles = (long)((n3[pd] + radix::tp_of(n) - 1) / radix::tp_of(n)) * n3[od];
-        if (!run(a, +1, ntiles)) return 1;
-        auto rhs = [&](int i, int j, int k) {   // 1-based cell
-          const long c = i + psy * j + psz * k;
-          const double wx = wq[0][i], wy = wq[1][j], wz = wq[2][k];
-          const double du = u[c] - u[c - 1], dv = v[c] - v[c - psy], dw = w[c] - w[c - psz];
-          double val = (dw * gq[2][k] * wx * wy + dv * gq[1][j] * wx * wz + du * gq[0][i] * wy * wz) * rdt;
-          if (i == 1) val += cb[0][0] * wy * wz;
-          if (i == n3[0]) val += cb[0][1] * wy * wz;
-          if (j == 1) val += cb[1][0] * wx * wz;
-          if (j == n3[1]) val += cb[1][1] * wx * wz;
-          if (k == 1) val += cb[2][0] * wx * wy;
-          if (k == n3[2]) val += cb[2][1] * wx * wy;
-          return val;
-        };
-        double err = 0.0, nrm = 0.0;
-        for (int k = 0; k < n3[2]; ++k) for (int j = 0; j < n3[1]; ++j) for (int i = 0; i < n3[0]; ++i) {
-          const int idx[3] = {i, j, k};
-          const int t = idx[axis];
-          double acc = 0.0;
-          for (int s2 = 0; s2 < n; ++s2) {
-            int id2[3] = {i, j, k};
-            id2[axis] = s2;
-            acc += Mx[(size_t)t * n + s2] * rhs(id2[0] + 1, id2[1] + 1, id2[2] + 1);
-          }
-          const double got = spec[idx[0] * sst[0] + idx[1] * sst[1] + idx[2] * sst[2]];
-          err = std::max(err, std::fabs(got - acc));
-          nrm = std::max(nrm, std::fabs(acc));
-        }
-        const double rel = err / nrm;
-        worst = std::max(worst, rel);
-        ++cases;
-        if (!(rel < 1e-13 * std::log2((double)n))) {
-          printf("FAIL fused fillps n=%d axis=%d kind=%d rel=%.3e\n", n, axis, kind, rel);
-          return 1;
-        }
-      }
   printf("OK %d cases, worst relative error %.3e\n", cases, worst);
   return 0;
 }
