@@ -37,7 +37,10 @@ def main():
             ("channel", 0, dict(dims=(world, 1, 1), ng=(8 * world, 6, 10))),
             ("channel", 0, dict(dims=(1, 1, world), ng=(12, 6, 10 * world), gr_z=0.0)),
             ("lshape", 1, {}),
-            ("dhc", 0, dict(impdiff=True, boussinesq=True))]
+            ("dhc", 0, dict(impdiff=True, boussinesq=True)),
+            # implicit diffusion in an FFT_AXIS build (solve_impdiff_field_fft): the reference's test case and a channel
+            ("dhc", 2, dict(impdiff=True, boussinesq=True)),
+            ("channel", 2, dict(dims=(world, 1, 1), ng=(8 * world, 8, 12), impdiff=True))]
     ok = True
     for kind, fa, kw in todo:
         from snac_b200.case import setup_case
@@ -48,10 +51,10 @@ def main():
             tmp = [tempfile.mkdtemp() if rank == 0 else None]
             dist.broadcast_object_list(tmp, 0)
             if rank == 0:
-                case = cases.make(kind, tmp[0], fft_axis=fa, **kw)
+                case = cases.make(kind, tmp[0], fft_axis=fa, impdiff=imp, boussinesq=bou, **kw)
             dist.barrier()
             if rank != 0:
-                case = setup_case(tmp[0], fft_axis=fa)
+                case = setup_case(tmp[0], fft_axis=fa, impdiff=imp, boussinesq=bou)
         nr = case.world.nrank
         owner = [r % world for r in range(nr)]
         g = Simulation(case, device=local, nproc=world, myproc=rank, rank_owner=owner, tol=1e-12, maxiter=200)
