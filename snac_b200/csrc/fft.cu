@@ -371,12 +371,16 @@ __global__ void __launch_bounds__(256) r2r_fast_kernel(const R2RArgs a) {
 }
 
 // register-radix kernels (fft_radix.cuh): one CTA per tile of 32 pencils
-template <int R1, int R2, bool FWD, bool SPLIT>
+template <int R1, int R2, bool FWD, bool SPLIT, bool STAGE = false>
 __global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS, FWD ? radix::Plan<R1, R2>::MINB_FWD : 0) r2r_radix_kernel(const R2RArgs a) {
   extern __shared__ __align__(16) double2 Zs[];
   const radix::Thread T = radix::thread_of<radix::Plan<R1, R2>::TP>(a, threadIdx.x, blockDim.x, blockIdx.x);
   if (FWD) {
-    radix::fwd_pass1<R1, R2, SPLIT>(a, Zs, T);
+    if (STAGE) {
+      radix::stage_io<R1, R2>(a, Zs, threadIdx.x, blockDim.x, blockIdx.x, true);
+      __syncthreads();
+    }
+    radix::fwd_pass1<R1, R2, SPLIT, STAGE>(a, Zs, T);
     __syncthreads();
     radix::run_pass<R1, R2, false>(a, Zs, T);
     __syncthreads();
@@ -391,39 +395,45 @@ __global__ void __launch_bounds__(radix::Plan<R1, R2>::THREADS, FWD ? radix::Pla
     __syncthreads();
     radix::run_pass<R1, R2, true>(a, Zs, T);
     __syncthreads();
-    radix::bwd_pass2<R1, R2, SPLIT>(a, Zs, T);
+    radix::bwd_pass2<R1, R2, SPLIT, STAGE>(a, Zs, T);
+    if (STAGE) {
+      __syncthreads();
+      radix::stage_io<R1, R2>(a, Zs, threadIdx.x, blockDim.x, blockIdx.x, false);
+    }
   }
 }
 
-template <int R1, int R2, bool FWD, bool SPLIT>
+template <int R1, int R2, bool FWD, bool SPLIT, bool STAGE>
 static void radix_go1(cudaStream_t st, const R2RArgs &a, long ntiles) {
   using P = radix::Plan<R1, R2>;
   static bool attr = false;
-  if (!attr && P::SMEM > 48 * 1024) {
-    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, FWD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+  if (!attr && P::SMEM > 40 * 1024) {
+    SNAC_CUDA(cudaFuncSetAttribute(r2r_radix_kernel<R1, R2, FWD, SPLIT, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
     attr = true;
   }
-  r2r_radix_kernel<R1, R2, FWD, SPLIT><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
+  r2r_radix_kernel<R1, R2, FWD, SPLIT, STAGE><<<(unsigned)ntiles, P::THREADS, P::SMEM, st>>>(a);
 }
 
 template <int R1, int R2>
-static void radix_go(cudaStream_t st, const R2RArgs &a, int dir, long ntiles) {
+static void radix_go(cudaStream_t st, const R2RArgs &a, int dir, long ntiles, bool stage) {
   const bool split = a.in_split != 0 || a.out_split != 0;
-  if (dir > 0) {
-    if (split) radix_go1<R1, R2, true, true>(st, a, ntiles); else radix_go1<R1, R2, true, false>(st, a, ntiles);
+  if (stage) {
+    if (dir > 0) { if (split) radix_go1<R1, R2, true, true, true>(st, a, ntiles); else radix_go1<R1, R2, true, false, true>(st, a, ntiles); }
+    else         { if (split) radix_go1<R1, R2, false, true, true>(st, a, ntiles); else radix_go1<R1, R2, false, false, true>(st, a, ntiles); }
   } else {
-    if (split) radix_go1<R1, R2, false, true>(st, a, ntiles); else radix_go1<R1, R2, false, false>(st, a, ntiles);
+    if (dir > 0) { if (split) radix_go1<R1, R2, true, true, false>(st, a, ntiles); else radix_go1<R1, R2, true, false, false>(st, a, ntiles); }
+    else         { if (split) radix_go1<R1, R2, false, true, false>(st, a, ntiles); else radix_go1<R1, R2, false, false, false>(st, a, ntiles); }
   }
 }
 
 // transform lengths served by the radix kernels: n = 2 R1 R2
-static bool radix_launch(cudaStream_t st, const R2RArgs &a, int dir, long ntiles) {
+static bool radix_launch(cudaStream_t st, const R2RArgs &a, int dir, long ntiles, bool stage) {
   switch (a.nt) {
-    case 32: radix_go<4, 4>(st, a, dir, ntiles); return true;
-    case 64: radix_go<8, 4>(st, a, dir, ntiles); return true;
-    case 128: radix_go<8, 8>(st, a, dir, ntiles); return true;
-    case 256: radix_go<16, 8>(st, a, dir, ntiles); return true;
-    case 512: radix_go<16, 16>(st, a, dir, ntiles); return true;
+    case 32: radix_go<4, 4>(st, a, dir, ntiles, stage); return true;
+    case 64: radix_go<8, 4>(st, a, dir, ntiles, stage); return true;
+    case 128: radix_go<8, 8>(st, a, dir, ntiles, stage); return true;
+    case 256: radix_go<16, 8>(st, a, dir, ntiles, stage); return true;
+    case 512: radix_go<16, 16>(st, a, dir, ntiles, stage); return true;
     default: return false;
   }
 }
@@ -470,11 +480,16 @@ void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const do
       return;
     }
   }
-  if (pl.fast && !a.in_lane_t && !a.out_lane_t && !staged_only) {
+  // the radix kernels: lanes along the pencils on both sides, or -- the transform axis at unit stride on the physical
+  // side (input of a forward, output of a backward transform), the pencils at unit stride on the spectral side -- with
+  // the physical tile staged through shared memory
+  const bool phys_lane_t = dir > 0 ? (a.in_lane_t && !a.out_lane_t && in_split <= 1 && ost[a.pd] == 1)
+                                   : (a.out_lane_t && !a.in_lane_t && out_split <= 1 && ist[a.pd] == 1);
+  if (pl.fast && ((!a.in_lane_t && !a.out_lane_t) || phys_lane_t) && !staged_only) {
     a.tab = pl.twiddle.p();
     a.tp = radix::tp_of(a.nt);
     const long nt16 = (long)((n3[a.pd] + a.tp - 1) / a.tp) * n3[a.od];
-    if (radix_launch(ctx.stream, a, dir, nt16)) {
+    if (radix_launch(ctx.stream, a, dir, nt16, phys_lane_t)) {
       ctx.launches++;
       SNAC_CUDA(cudaGetLastError());
       return;
@@ -484,15 +499,15 @@ void r2r_execute(Ctx &ctx, const R2RPlan &pl, int dir, const int n3[3], const do
   if (pl.fast) {
     a.tab = pl.twiddle.p();
     if (dir > 0) {
-      if (smem > 48 * 1024) SNAC_CUDA(cudaFuncSetAttribute(r2r_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) SNAC_CUDA(cudaFuncSetAttribute(r2r_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       r2r_fast_kernel<true><<<(unsigned)ntiles, 256, smem, ctx.stream>>>(a);
     } else {
-      if (smem > 48 * 1024) SNAC_CUDA(cudaFuncSetAttribute(r2r_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) SNAC_CUDA(cudaFuncSetAttribute(r2r_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       r2r_fast_kernel<false><<<(unsigned)ntiles, 256, smem, ctx.stream>>>(a);
     }
   } else {
     a.tab = dir > 0 ? pl.mat_fwd.p() : pl.mat_bwd.p();
-    if (smem > 48 * 1024) SNAC_CUDA(cudaFuncSetAttribute(r2r_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) SNAC_CUDA(cudaFuncSetAttribute(r2r_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     r2r_dense_kernel<<<(unsigned)ntiles, 256, smem, ctx.stream>>>(a);
   }
   ctx.launches++;

@@ -192,7 +192,9 @@ SNAC_HD bool is_makhoul(int kind) { return kind == K_REDFT10 || kind == K_RODFT1
 SNAC_HD bool is_sine(int kind) { return kind == K_RODFT10 || kind == K_RODFT01; }
 
 // ---- forward ---------------------------------------------------------------------------------
-template <int R1, int R2, bool SPLIT>
+// STAGE: the tile was brought into Z by stage_in (the transform axis is at unit stride on the physical side): element e
+// of the permuted sequence, sign included, sits where this thread's own output for the same e goes
+template <int R1, int R2, bool SPLIT, bool STAGE = false>
 SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
   using P = Plan<R1, R2>;
   if (!T.valid) return;
@@ -207,6 +209,11 @@ SNAC_HD void fwd_pass1(const R2RArgs &a, double2 *Z, const Thread &T) {
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       const int e = j + r * P::S1;
+      if (STAGE) {
+        const double2 z = Z[e * P::TP + T.p];
+        v[r] = Cx{z.x, z.y};
+        continue;
+      }
       const int t0 = tof(2 * e, P::N, makhoul), t1 = tof(2 * e + 1, P::N, makhoul);
       double x0 = R2R_IN_ATS(t0, T.ib, isa), x1 = R2R_IN_ATS(t1, T.ib, isa);
       if (sine && (t0 & 1)) x0 = -x0;
@@ -361,8 +368,10 @@ SNAC_HD void bwd_tangle(const R2RArgs &a, double2 *Z, const Thread &T) {
   }
 }
 
-template <int R1, int R2, bool SPLIT>
-SNAC_HD void bwd_pass2(const R2RArgs &a, const double2 *Z, const Thread &T) {   // radix R1 at stride S1, then the store
+// STAGE: the results go back into the thread's own slots of Z (element e of the permuted sequence, scaled, sign
+// included) and leave through stage_out
+template <int R1, int R2, bool SPLIT, bool STAGE = false>
+SNAC_HD void bwd_pass2(const R2RArgs &a, double2 *Z, const Thread &T) {   // radix R1 at stride S1, then the store
   using P = Plan<R1, R2>;
   if (!T.valid) return;
   const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
@@ -385,8 +394,42 @@ SNAC_HD void bwd_pass2(const R2RArgs &a, const double2 *Z, const Thread &T) {   
       double x0 = v[r].x * a.scale, x1 = v[r].y * a.scale;
       if (sine && (t0 & 1)) x0 = -x0;
       if (sine && (t1 & 1)) x1 = -x1;
+      if (STAGE) { Z[e * P::TP + T.p] = make_double2(x0, x1); continue; }
       R2R_OUT_ATS(t0, T.ob, osa) = x0;
       R2R_OUT_ATS(t1, T.ob, osa) = x1;
+    }
+  }
+}
+
+// ---- transform axis at unit stride on the physical side (FFT_AXIS = 1) -----------------------------------------
+// The pencils of a tile are rows of the physical array: lanes along the pencils would read 8 bytes per row.  The
+// tile goes through shared memory instead: a quarter warp takes 4 consecutive elements (64 contiguous bytes) of 8
+// pencils and writes them as one conflict-free 128-byte shared-memory wavefront per element, into the slots from which
+// (into which) the first (last) radix pass of the owning thread reads (writes) them.
+template <int R1, int R2>
+SNAC_HD void stage_io(const R2RArgs &a, double2 *Z, int tid, int nthr, int tile, bool in) {
+  using P = Plan<R1, R2>;
+  constexpr int TP = P::TP, M = P::M, N = P::N;
+  const bool makhoul = is_makhoul(a.kind), sine = is_sine(a.kind);
+  const int ntp = (a.n[a.pd] + TP - 1) / TP;
+  const int ip0 = (tile % ntp) * TP, o = tile / ntp;
+  const long st_ax = in ? a.ist[a.axis] : a.ost[a.axis];
+  const long st_pd = in ? a.ist[a.pd] : a.ost[a.pd], st_od = in ? a.ist[a.od] : a.ost[a.od];
+  for (int idx = tid; idx < M * TP; idx += nthr) {
+    const int p = (idx & 7) + 8 * ((idx >> 5) % (TP / 8));
+    const int e = ((idx >> 3) & 3) + 4 * (idx / (4 * TP));
+    if (ip0 + p >= a.n[a.pd]) continue;
+    const long base = (long)(ip0 + p) * st_pd + (long)o * st_od;
+    const int t0 = tof(2 * e, N, makhoul), t1 = tof(2 * e + 1, N, makhoul);
+    if (in) {
+      double x0 = a.inp[0][base + t0 * st_ax], x1 = a.inp[0][base + t1 * st_ax];
+      if (sine && (t0 & 1)) x0 = -x0;
+      if (sine && (t1 & 1)) x1 = -x1;
+      Z[e * TP + p] = make_double2(x0, x1);
+    } else {
+      const double2 z = Z[e * TP + p];
+      a.outp[0][base + t0 * st_ax] = z.x;
+      a.outp[0][base + t1 * st_ax] = z.y;
     }
   }
 }

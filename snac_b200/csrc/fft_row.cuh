@@ -282,7 +282,7 @@ static void row_go(cudaStream_t st, const R2RArgs &a, long nrows) {
   static bool attr = false;
   static int per_sm = 1, sms = 148;
   if (!attr) {
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024)
       SNAC_CUDA(cudaFuncSetAttribute(r2r_row_kernel<R, FWD, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0;
     cudaGetDevice(&dev);

@@ -465,7 +465,9 @@ void launch_mg_coarse(cudaStream_t st, const CoarseArgs &a, bool single) {
   const long top = (long)a.lev[0].n1 * a.lev[0].n2;
   int nt = 128;
   while (nt < 1024 && nt * 8 < top) nt *= 2;   // about eight cells of the top level per thread
-  static size_t cap[2] = {48 * 1024, 48 * 1024};
+  // opt in as soon as the dynamic part alone comes near 48 KB: the kernel's static shared memory counts against the
+  // same default limit (a 64 x 64 hierarchy in FP32 asks for 48 784 B and was refused with "invalid argument")
+  static size_t cap[2] = {40 * 1024, 40 * 1024};
   if (smem > cap[single]) {
     if (single) SNAC_CUDA(cudaFuncSetAttribute(mg_coarse_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else SNAC_CUDA(cudaFuncSetAttribute(mg_coarse_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -473,6 +475,11 @@ void launch_mg_coarse(cudaStream_t st, const CoarseArgs &a, bool single) {
   }
   if (single) mg_coarse_kernel<float><<<a.nq, nt, smem, st>>>(a);
   else mg_coarse_kernel<double><<<a.nq, nt, smem, st>>>(a);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    throw Error(std::string("mg_coarse_kernel launch failed: ") + cudaGetErrorString(e) + " (planes " + std::to_string(a.nq) + ", threads " +
+                std::to_string(nt) + ", dynamic shared memory " + std::to_string(smem) + " B, " + std::to_string(a.nlev) + " levels from " +
+                std::to_string(a.lev[0].n1) + " x " + std::to_string(a.lev[0].n2) + ")");
 }
 
 }  // namespace snac

@@ -20,13 +20,25 @@ static void emulate(const R2RArgs &a, int dir, long ntiles) {
     auto phase = [&](auto fn) {
       for (int tid = 0; tid < P::THREADS; ++tid) fn(radix::thread_of<P::TP>(a, tid, P::THREADS, (int)tile));
     };
+    const bool stage = dir > 0 ? a.in_lane_t != 0 : a.out_lane_t != 0;   // the transform axis is at unit stride on the physical side
+    auto stage_phase = [&](bool in) {
+      for (int tid = 0; tid < P::THREADS; ++tid) radix::stage_io<R1, R2>(a, Z.data(), tid, P::THREADS, (int)tile, in);
+    };
     if (dir > 0) {
+      if (stage) {
+        stage_phase(true);
+        phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, true, true>(a, Z.data(), T); });
+      } else
       phase([&](const radix::Thread &T) { radix::fwd_pass1<R1, R2, true>(a, Z.data(), T); });
       phase([&](const radix::Thread &T) { radix::run_pass<R1, R2, false>(a, Z.data(), T); });
       phase([&](const radix::Thread &T) { radix::fwd_untangle<R1, R2, true>(a, Z.data(), T); });
     } else {
       phase([&](const radix::Thread &T) { radix::bwd_tangle<R1, R2, true>(a, Z.data(), T); });
       phase([&](const radix::Thread &T) { radix::run_pass<R1, R2, true>(a, Z.data(), T); });
+      if (stage) {
+        phase([&](const radix::Thread &T) { radix::bwd_pass2<R1, R2, true, true>(a, Z.data(), T); });
+        stage_phase(false);
+      } else
       phase([&](const radix::Thread &T) { radix::bwd_pass2<R1, R2, true>(a, Z.data(), T); });
     }
   }
@@ -50,16 +62,17 @@ int main() {
   double worst = 0.0;
   int cases = 0;
   for (int n : {32, 64, 128, 256, 512})
-    for (int axis : {1, 2})
+    for (int axis : {0, 1, 2})   // axis 0: unit stride on the physical side, the tile is staged through shared memory
       for (int kind : kinds)
         for (int split : {1, 2, -2, -4}) {   // one array; two consecutive chunks; cyclic over two / four arrays
-          // box: 21 pencils along x (a partial second tile), 3 along the other direction
-          int n3[3] = {21, 3, 3};
+          // box: 21 pencils along pd (a partial second tile), 3 along the other direction
+          int n3[3] = {3, 3, 3};
+          const int pd = axis == 0 ? 1 : 0, od = 3 - axis - pd;
+          n3[pd] = 21;
           n3[axis] = n;
-          const int pd = 0, od = 3 - axis - pd;
           const bool fwd = (kind == K_R2HC || kind == K_REDFT10 || kind == K_RODFT10);
           // physical array: ghosted, padded; spectral array: (x, other, q) as the solver wants it
-          const long psy = 40, psz = psy * (n3[1] + 2);
+          const long psy = n3[0] + 19, psz = psy * (n3[1] + 2);
           const long pst[3] = {1, psy, psz};
           long sst[3];
           sst[pd] = 1; sst[od] = 24; sst[axis] = 24L * n3[od];
@@ -77,7 +90,7 @@ int main() {
           // in its own array (here: the same layout, second half in spec2)
           for (int d = 0; d < 3; ++d) { a.n[d] = n3[d]; a.ist[d] = fwd ? pst[d] : sst[d]; a.ost[d] = fwd ? sst[d] : pst[d]; }
           a.axis = axis; a.nt = n; a.tp = radix::tp_of(n); a.pd = pd; a.od = od; a.kind = kind;
-          a.in_lane_t = a.out_lane_t = 0; a.scale = 0.75; a.tab = tab.data(); a.chunk = chunk;
+          a.in_lane_t = (fwd && axis == 0) ? 1 : 0; a.out_lane_t = (!fwd && axis == 0) ? 1 : 0; a.scale = 0.75; a.tab = tab.data(); a.chunk = chunk;
           a.ns_mask = ncyc ? ncyc - 1 : 0; a.ns_shift = ncyc == 4 ? 2 : (ncyc == 2 ? 1 : 0);
           std::vector<double> in((size_t)n3[0] * n3[1] * n3[2]);
           for (auto &v : in) v = U(rng);
