@@ -954,10 +954,13 @@ static void substep(Ctx &ctx, int irk, double dt) {
 
 using namespace snac;
 
+// every entry point ends with a look at the launch status: a refused launch (bad configuration) is not sticky and
+// would otherwise surface at some later, unrelated check -- or never
 #define SNAC_TRY(h, ...)                          \
   if (!(h)) return -2;                            \
   try {                                           \
     __VA_ARGS__;                                  \
+    SNAC_CUDA(cudaGetLastError());                \
     return 0;                                     \
   } catch (const std::exception &e) {             \
     (h)->ctx.err = e.what();                      \
