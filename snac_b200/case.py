@@ -28,7 +28,11 @@ class Case:
 
 def setup_case(rundir: str = ".", fft_axis: int = 0, impdiff: bool = False, boussinesq: bool = False,
                params: Params = None) -> Case:
-    p = params if params is not None else read_input(rundir, fft_axis, impdiff, boussinesq)
+    auto = fft_axis in ("auto", -1)   # a build of the reference that accepts this input (param.pick_fft_axis)
+    p = params if params is not None else read_input(rundir, 0 if auto else fft_axis, impdiff, boussinesq)
+    if auto and params is None:
+        from .param import pick_fft_axis
+        p.fft_axis = pick_fft_axis(p)
     world = initmpi(p)
     bg = block_grids(p, rundir)
     g = box_grids(p, world, bg)

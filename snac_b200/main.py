@@ -6,7 +6,7 @@ Mirrors ``src/main.f90``: start-up and restart (``:195-253,428-438,542-568,633-6
 criteria, ``chkdt``/``chkdiv`` every ``icheck`` steps and the output cadences (``:893-1144``).  All numerics are in
 ``libsnacb200.so`` (``snac_step``, ``snac_chkdt``, ``snac_chkdiv``, ``snac_out1d``); this file is control flow and files.
 
-    python -m snac_b200.main RUNDIR [--fft-axis {0,1,2,3}] [--impdiff] [--boussinesq]
+    python -m snac_b200.main RUNDIR [--fft-axis {0,1,2,3,auto}] [--impdiff] [--boussinesq]
 
 The compile-time switches of the reference (``FFT_AXIS``, ``_IMPDIFF``, ``_BOUSSINESQ_BUOYANCY``) are command-line
 options here.  One process drives one GPU; with ``torchrun`` every process owns the boxes ``rank % nproc``.
@@ -124,7 +124,9 @@ def run(rundir, fft_axis=0, impdiff=False, boussinesq=False, device=0, nproc=1, 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("rundir")
-    ap.add_argument("--fft-axis", type=int, default=0, choices=(0, 1, 2, 3))
+    ap.add_argument("--fft-axis", default="0", choices=("0", "1", "2", "3", "auto"),
+                    help="FFT_AXIS of the reference's build; auto: a build the reference accepts for this input (transforms along a "
+                         "uniform, undecomposed direction), else 0")
     ap.add_argument("--impdiff", action="store_true")
     ap.add_argument("--boussinesq", action="store_true")
     a = ap.parse_args(argv)
@@ -134,7 +136,7 @@ def main(argv=None):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("gloo")
-    sim = run(a.rundir, a.fft_axis, a.impdiff, a.boussinesq, device=local, nproc=nproc, myproc=myproc)
+    sim = run(a.rundir, "auto" if a.fft_axis == "auto" else int(a.fft_axis), a.impdiff, a.boussinesq, device=local, nproc=nproc, myproc=myproc)
     sim.close()
 
 

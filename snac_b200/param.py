@@ -299,6 +299,44 @@ class Params:
                          for b in self.blocks))
 
 
+def fft_axes_allowed(p: "Params") -> List[int]:
+    """The FFT_AXIS builds of the reference that accept this input, as 1-based axes (``chk_grid_fft``,
+    src/sanity.f90:66-100: the direction is not decomposed, has the same extent and number of points in every block and
+    a uniform grid; ``find_fft`` / ``eigenvalues``, src/fft.f90:96-189: the pressure boundary-condition pair has a
+    transform and eigenvalues -- 'DN' has none).  With implicit diffusion the velocity and scalar pairs must have them too."""
+    out = []
+    for d in range(3):
+        ok = len(p.blocks) > 0
+        b0 = p.blocks[0] if p.blocks else None
+        pairs = set()
+        for b in p.blocks:
+            ok = ok and int(b.dims[d]) == 1 and float(b.gr[d]) == 0.0
+            ok = ok and int(b.ng[d]) == int(b0.ng[d]) and float(b.lmin[d]) == float(b0.lmin[d]) and float(b.lmax[d]) == float(b0.lmax[d])
+            pairs.add(str(b.cbcpre[0, d]) + str(b.cbcpre[1, d]))
+            if p.impdiff:
+                for c in range(3):
+                    pairs.add(str(b.cbcvel[0, d, c]) + str(b.cbcvel[1, d, c]))
+                for i in range(p.nscal):
+                    pairs.add(str(b.cbcscal[0, d, i]) + str(b.cbcscal[1, d, i]))
+        ok = ok and len(pairs) > 0 and pairs <= {"FF", "NN", "DD", "ND"}
+        # every block must carry the same pressure pair along the transform direction (one plan for the run)
+        ok = ok and len({str(b.cbcpre[0, d]) + str(b.cbcpre[1, d]) for b in p.blocks}) == 1
+        if ok:
+            out.append(d + 1)
+    return out
+
+
+def pick_fft_axis(p: "Params") -> int:
+    """``--fft-axis auto``: FFT_AXIS is a build option of the reference and a run-time field here; when the input does not
+    say, take a build the reference itself would accept for this case (the transform path replaces a 3-D solve by
+    per-wavenumber plane solves, direct where the planes are separable), z before y before x; 0 if none applies."""
+    ok = fft_axes_allowed(p)
+    for d in (3, 2, 1):
+        if d in ok:
+            return d
+    return 0
+
+
 def read_input(rundir: str = ".", fft_axis: int = 0, impdiff: bool = False,
                boussinesq: bool = False, dns_file: str = "dns.nml",
                blocks_file: str = "blocks.nml") -> Params:
