@@ -66,7 +66,8 @@ typedef struct snac_params {
   const int *rank_owner;  /* [nrank] process owning each box (NULL: all owned by process 0) */
   int periods[3];         /* global extent in periodic directions, else 0 (src/initmpi.f90:107-113) */
   int fft_axis;           /* 0: 3-D solve; 1,2,3: transforms along x,y,z (FFT_AXIS build option) */
-  int impdiff;            /* IMPDIFF build option */
+  int impdiff;            /* IMPDIFF build option; with fft_axis > 0 the Helmholtz systems of solve_impdiff_field_fft
+                           * (src/solve_helmholtz.f90:32-100) are solved in 3-D: the same linear systems */
   int boussinesq;         /* BOUSSINESQ_BUOYANCY build option */
   int nscal;
   double visc;            /* 1/visci (src/param.f90:175) */
@@ -80,7 +81,7 @@ typedef struct snac_params {
   double scalf[SNAC_MAX_SCAL];
   double hypre_tol;       /* relative residual tolerance of the linear solves (src/param.f90:15-17) */
   int hypre_maxiter;
-  int hypre_solver_i;     /* accepted for compatibility; the solver is always geometric multigrid */
+  int hypre_solver_i;     /* accepted for compatibility; the solver is geometric multigrid or the direct plane solver */
   /* multigrid tuning (0 = default) */
   int mg_npre, mg_npost, mg_nbottom;
   int mg_generic;         /* 1: always use the general multi-box multigrid kernels */
