@@ -135,6 +135,15 @@ SNAC_API const char *snac_last_error(const snac_handle *h);   /* h may be NULL: 
 /* ---- field transfer (host layout: see header comment) ------------------------------------ */
 SNAC_API int snac_upload(snac_handle *h, int rank, int field, const double *host);
 SNAC_API int snac_download(snac_handle *h, int rank, int field, double *host);
+/* Outputs and checkpoints without stopping the time loop (the reference writes them with blocking MPI-IO from the host
+ * arrays, src/load.f90:84-187, src/output.f90:227-257): snac_download_async packs what the field holds NOW into a device
+ * staging array in stream order, starts the device -> host copy on a copy stream and returns a ticket; the caller goes on
+ * stepping.  snac_download_wait blocks until that copy has landed; it may be called from another host thread (a file
+ * writer).  `host`: layout of snac_download; pinned memory (snac_host_alloc) lets the copy overlap with the kernels. */
+SNAC_API int snac_download_async(snac_handle *h, int rank, int field, double *host, int *ticket);
+SNAC_API int snac_download_wait(snac_handle *h, int ticket);
+SNAC_API void *snac_host_alloc(size_t bytes);
+SNAC_API void snac_host_free(void *p);
 
 /* ---- fine-grained entry points, 1:1 with the reference subroutines -------------------------
  * Each acts on all boxes owned by the process. */

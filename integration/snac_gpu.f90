@@ -21,7 +21,7 @@ module mod_snac_gpu
             snac_boundp, snac_set_inflow, snac_inflow, snac_fillps, snac_updt_rhs, snac_fft, &
             snac_solve_n_helmholtz_2d, snac_solve_helmholtz, snac_correc, snac_updt_pressure, snac_chkdt, &
             snac_chkdiv, snac_out1d, snac_out2d, snac_step, snac_solver_stats, snac_solver_mean_iters, &
-            snac_plane_solver, snac_sync
+            snac_plane_solver, snac_sync, snac_download_async, snac_download_wait, snac_host_alloc, snac_host_free
   integer(c_int), parameter, public :: SNAC_ABI_VERSION = 2
   integer(c_int), parameter, public :: SNAC_MAX_SCAL = 8
   integer(c_int), parameter, public :: SNAC_FIELD_U = 0, SNAC_FIELD_V = 1, SNAC_FIELD_W = 2, SNAC_FIELD_P = 3, &
@@ -101,6 +101,27 @@ module mod_snac_gpu
       integer(c_int), value :: rank, field
       real(c_double), intent(inout) :: host(*)
     end function snac_download
+    ! outputs and checkpoints without stopping the time loop: `host` in pinned memory (snac_host_alloc + c_f_pointer)
+    integer(c_int) function snac_download_async(h, rank, field, host, ticket) bind(C, name='snac_download_async')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+      integer(c_int), value :: rank, field
+      type(c_ptr), value :: host
+      integer(c_int), intent(out) :: ticket
+    end function snac_download_async
+    integer(c_int) function snac_download_wait(h, ticket) bind(C, name='snac_download_wait')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+      integer(c_int), value :: ticket
+    end function snac_download_wait
+    type(c_ptr) function snac_host_alloc(bytes) bind(C, name='snac_host_alloc')
+      import :: c_ptr, c_size_t
+      integer(c_size_t), value :: bytes
+    end function snac_host_alloc
+    subroutine snac_host_free(p) bind(C, name='snac_host_free')
+      import :: c_ptr
+      type(c_ptr), value :: p
+    end subroutine snac_host_free
     ! ---- fine-grained entry points, 1:1 with the reference subroutines ---------------------------
     integer(c_int) function snac_rk_mom(h, irk, dt) bind(C, name='snac_rk_mom')                 ! src/rk.f90:7-128
       import :: c_int, c_ptr, c_double

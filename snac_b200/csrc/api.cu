@@ -678,6 +678,44 @@ static void transfer(Ctx &ctx, int rank, int field, double *host, bool up) {
   SNAC_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
+// Outputs and checkpoints without stopping the time loop (the reference writes
+// them with blocking MPI-IO from the host arrays, src/load.f90:84-187, src/output.f90:227-257): what the field holds
+// NOW is packed into a dense staging array in stream order, the device -> host copy runs on a copy stream, and the
+// caller gets a ticket to wait on -- from any host thread, it touches nothing but the ticket's event.
+static int download_async(Ctx &ctx, int rank, int field, double *host) {
+  Box &b = ctx.box_of_rank(rank);
+  if (ctx.prm.fft_axis > 0 && (field == SNAC_FIELD_PO || field == SNAC_FIELD_RHS_HAT))
+    throw Error("download_async: spectral fields are not supported (use snac_download)");
+  bool dummy;
+  Field3 *f = field == SNAC_FIELD_RHS_HAT ? &b.rhs : field_of(ctx, b, field, dummy);
+  if (!ctx.copy_stream) SNAC_CUDA(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
+  int slot = -1;
+  for (int q = 0; q < Ctx::MAX_ASYNC && slot < 0; ++q) {
+    Ctx::AsyncSlot &S = ctx.async_slot[q];
+    if (!S.done) {
+      SNAC_CUDA(cudaEventCreateWithFlags(&S.packed, cudaEventDisableTiming));
+      SNAC_CUDA(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+      slot = q;
+    } else if (cudaEventQuery(S.done) == cudaSuccess) {
+      slot = q;
+    }
+  }
+  (void)cudaGetLastError();   // cudaErrorNotReady of the queries above is not an error
+  if (slot < 0) throw Error("download_async: too many copies in flight (wait for some of them)");
+  Ctx::AsyncSlot &S = ctx.async_slot[slot];
+  const int w = b.g.n[0] + 2, hh = b.g.n[1] + 2, dpt = b.g.n[2] + 2;
+  const size_t dense = (size_t)w * hh * dpt;
+  if (S.stage.elems < dense) S.stage.alloc(dense);
+  dim3 blk(32, 8, 1), gfull((w + 31) / 32, (hh + 7) / 8, dpt);
+  permute_copy_kernel<<<gfull, blk, 0, ctx.stream>>>(S.stage.raw, 1, w, (long)w * hh, f->p, 1, b.g.sy, b.g.sz, w, hh, dpt);
+  ctx.launches++;
+  SNAC_CUDA(cudaEventRecord(S.packed, ctx.stream));
+  SNAC_CUDA(cudaStreamWaitEvent(ctx.copy_stream, S.packed, 0));
+  SNAC_CUDA(cudaMemcpyAsync(host, S.stage.raw, dense * sizeof(double), cudaMemcpyDeviceToHost, ctx.copy_stream));
+  SNAC_CUDA(cudaEventRecord(S.done, ctx.copy_stream));
+  return slot;
+}
+
 // ---- pieces of the sub-step ------------------------------------------------------------------
 static void do_rk_mom(Ctx &ctx, int irk, double dt) {
   ctx.vel_epoch++;
@@ -1071,6 +1109,11 @@ int snac_comm_connect(snac_handle *h, const void *blobs, int nblobs) {
 int snac_finalize(snac_handle *h) {
   if (!h) return -2;
   cudaStreamSynchronize(h->ctx.stream);
+  if (h->ctx.copy_stream) { cudaStreamSynchronize(h->ctx.copy_stream); cudaStreamDestroy(h->ctx.copy_stream); }
+  for (auto &S : h->ctx.async_slot) {
+    if (S.packed) cudaEventDestroy(S.packed);
+    if (S.done) cudaEventDestroy(S.done);
+  }
   if (h->ctx.h_red) cudaFreeHost(h->ctx.h_red);
   if (h->ctx.d_slots) cudaFree(h->ctx.d_slots);
   h->ctx.comm.release();
@@ -1085,6 +1128,21 @@ int snac_upload(snac_handle *h, int rank, int field, const double *host) {
 }
 int snac_download(snac_handle *h, int rank, int field, double *host) {
   SNAC_TRY(h, transfer(h->ctx, rank, field, host, false))
+}
+
+int snac_download_async(snac_handle *h, int rank, int field, double *host, int *ticket) {
+  SNAC_TRY(h, *ticket = download_async(h->ctx, rank, field, host))
+}
+int snac_download_wait(snac_handle *h, int ticket) {
+  if (!h || ticket < 0 || ticket >= Ctx::MAX_ASYNC || !h->ctx.async_slot[ticket].done) return -2;
+  return cudaEventSynchronize(h->ctx.async_slot[ticket].done) == cudaSuccess ? 0 : -1;
+}
+void *snac_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void snac_host_free(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 int snac_rk_mom(snac_handle *h, int irk, double dt) { SNAC_TRY(h, do_rk_mom(h->ctx, irk, dt)) }

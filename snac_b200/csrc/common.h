@@ -557,6 +557,12 @@ struct Ctx {
   std::unique_ptr<MGSolver> ssolver[SNAC_MAX_SCAL];
   double fs[SNAC_MAX_SCAL] = {0};                   // accumulated scalar forcing (src/main.f90:913)
   // reductions
+  // snac_download_async: the field is packed into a staging array of its own in stream order, copied to the host on a
+  // copy stream; a slot is free again once its copy has completed
+  struct AsyncSlot { DevBuf stage; cudaEvent_t packed = nullptr, done = nullptr; };
+  static constexpr int MAX_ASYNC = 32;
+  AsyncSlot async_slot[MAX_ASYNC];
+  cudaStream_t copy_stream = nullptr;
   DevBuf xfer;              // dense staging buffer of snac_upload / snac_download
   DevBuf red;               // scratch for chkdt/chkdiv
   double *h_red = nullptr;  // pinned

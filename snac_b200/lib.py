@@ -66,6 +66,10 @@ EXPORTS = {
     "snac_last_error": (C.c_char_p, [C.c_void_p]),
     "snac_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "snac_download": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "snac_download_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "snac_download_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "snac_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "snac_host_free": (None, [C.c_void_p]),
     "snac_rk_mom": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "snac_rk_scal": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "snac_bounduvw": (C.c_int, [C.c_void_p, C.c_int]),

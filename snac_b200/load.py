@@ -160,6 +160,36 @@ def write_checkpoint(sim, datadir: str, basename: str = "fld", ranks=None) -> No
                      istep=sim.istep, write_info=first)
 
 
+def write_checkpoint_async(sim, datadir: str, basename: str = "fld", ranks=None):
+    """``write_checkpoint`` without stopping the time loop: the fields as they are NOW are packed on the device and copied to
+    pinned host memory on a copy stream (``snac_download_async``); a writer thread waits for each copy and writes the same
+    files.  Returns the thread: ``join()`` it before the files are read, linked or overwritten."""
+    import threading
+
+    from . import lib as L
+    os.makedirs(datadir, exist_ok=True)
+    time, istep = sim.time, sim.istep
+    jobs = []
+    for r in (sim.ranks if ranks is None else ranks):
+        ib, ng, lo1, hi1, first = _block_frame(sim.case, r)
+        stem = os.path.join(datadir, f"{basename}_b_{ib + 1:03d}")
+        fields = [(f"{stem}_{name}.bin", fid) for name, fid in FIELD_SUFFIX]
+        fields += [(f"{stem}_s_{i + 1:03d}.bin", L.FIELD_S0 + i) for i in range(sim.case.params.nscal)]
+        for fname, fid in fields:
+            arr, ticket, free = sim.download_async(r, fid)
+            jobs.append((fname, ng, lo1, hi1, arr, ticket, free, first))
+
+    def writer():
+        for fname, ng, lo1, hi1, arr, ticket, free, first in jobs:
+            sim.download_wait(ticket)
+            load_one("w", fname, ng, lo1, hi1, arr, time=time, istep=istep, write_info=first)
+            free()
+
+    th = threading.Thread(target=writer, name="snac-checkpoint-writer")
+    th.start()
+    return th
+
+
 def read_checkpoint(sim, datadir: str, basename: str = "fld", ranks=None) -> None:
     """Restart (src/main.f90:542-556): fields into the device arrays (ghost cells are filled by the first
     bounduvw/boundp, as in the reference), ``time`` and ``istep`` from the trailer."""

@@ -59,6 +59,27 @@ def run(rundir, fft_axis=0, impdiff=False, boussinesq=False, device=0, nproc=1, 
     if root:
         print(f"dt_cfl = {sim.dt_cfl} dt = {sim.dt}", file=log)
     savecounter, is_done, kill = 0, False, False
+    writer = None   # the checkpoint being written by a thread while the time loop goes on (load.write_checkpoint_async)
+
+    def finish_checkpoint():
+        """joins the writer, then what needs every box of the files on disk: the barrier and the symbolic links"""
+        nonlocal writer
+        if writer is None:
+            return
+        th, base, stamp = writer
+        writer = None
+        th.join()
+        barrier()                                               # every box of a file is on disk before anything reads or links it
+        if not P.is_overwrite_save and root:                    # fld_* -> last checkpoint (symbolic links)
+            for ib in range(len(P.blocks)):
+                for suffix in ["u", "v", "w", "p"] + [f"s_{i + 1:03d}" for i in range(P.nscal)]:
+                    link = os.path.join(datadir, f"fld_b_{ib + 1:03d}_{suffix}.bin")
+                    if os.path.lexists(link):
+                        os.remove(link)
+                    os.symlink(f"{base}_b_{ib + 1:03d}_{suffix}.bin", link)
+        if root:
+            print(f"*** Checkpoint saved at time = {stamp[0]} time step = {stamp[1]}. ***", file=log)
+
     twi = _time.time()
     while not is_done:                                          # src/main.f90:893-1144
         sim.istep += 1
@@ -107,17 +128,11 @@ def run(rundir, fft_axis=0, impdiff=False, boussinesq=False, device=0, nproc=1, 
                     base = f"fld_{ichkpt:04d}"
                     if root:
                         out0d(os.path.join(datadir, "log_saves.out"), (1.0 * sim.istep, sim.time, 1.0 * ichkpt))
-            load.write_checkpoint(sim, datadir, basename=base)
-            barrier()                                           # every box of a file is on disk before anything reads or links it
-            if not P.is_overwrite_save and root:                # fld_* -> last checkpoint (symbolic links)
-                for ib in range(len(P.blocks)):
-                    for suffix in ["u", "v", "w", "p"] + [f"s_{i + 1:03d}" for i in range(P.nscal)]:
-                        link = os.path.join(datadir, f"fld_b_{ib + 1:03d}_{suffix}.bin")
-                        if os.path.lexists(link):
-                            os.remove(link)
-                        os.symlink(f"{base}_b_{ib + 1:03d}_{suffix}.bin", link)
-            if root:
-                print(f"*** Checkpoint saved at time = {sim.time} time step = {sim.istep}. ***", file=log)
+            finish_checkpoint()                                 # (the previous one, if it is still being written)
+            writer = (load.write_checkpoint_async(sim, datadir, basename=base), base, (sim.time, sim.istep))
+            if is_done:
+                finish_checkpoint()
+    finish_checkpoint()
     return sim
 
 

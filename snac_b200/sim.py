@@ -135,6 +135,25 @@ class Simulation:
         self._chk(self.lib.snac_download(self.h, r, field, a.ctypes.data_as(C.c_void_p)))
         return a
 
+    def download_async(self, r, field):
+        """Starts the copy of what the field holds now into pinned host memory and returns ``(array, ticket, free)``: the
+        time loop may go on; ``download_wait(ticket)`` (any thread) blocks until ``array`` is complete, ``free()`` releases
+        the pinned memory."""
+        shp = self.shape(r)
+        n = int(np.prod(shp))
+        ptr = self.lib.snac_host_alloc(n * 8)
+        if not ptr:
+            raise L.SnacError("snac_host_alloc failed")
+        a = np.ctypeslib.as_array((C.c_double * n).from_address(ptr)).reshape(shp, order="F")
+        t = C.c_int(-1)
+        self._chk(self.lib.snac_download_async(self.h, r, field, C.c_void_p(ptr), C.byref(t)))
+        lib = self.lib
+        return a, t.value, (lambda: lib.snac_host_free(C.c_void_p(ptr)))
+
+    def download_wait(self, ticket):
+        if self.lib.snac_download_wait(self.h, ticket) != 0:
+            raise L.SnacError("snac_download_wait failed")
+
     def set_fields(self, ini):
         """ini[r] = dict(u=,v=,w=,p=,s=[...]) of ghosted Fortran-order arrays."""
         for r in self.ranks:

@@ -528,3 +528,32 @@ def test_duct_blocks_without_merging_go_through_the_block_interfaces(tmp_path, m
     (halo exchange of the iterate across block interfaces on every level), against the exact solution"""
     monkeypatch.setenv("SNAC_MERGE_BLOCKS", "0")
     _solve_and_compare(tmp_path, "duct", 1, {}, False)
+
+
+def test_asynchronous_checkpoint_holds_the_fields_of_its_step(tmp_path):
+    """snac_download_async / load.write_checkpoint_async: the files hold the fields as they were when the checkpoint was
+    requested, although the time loop went on while they were copied and written."""
+    from snac_b200 import load
+    from snac_b200.sim import Simulation
+    case = cases.make("channel", str(tmp_path / "case"), fft_axis=2)
+    g = Simulation(case, tol=1e-10, maxiter=100)
+    g.set_fields(initial_fields(case, noise=True))
+    g.init_bc(); g.set_dt()
+    for _ in range(2):
+        g.step()
+    ref = {(r, k): g.download(r, fid) for r in g.ranks for k, fid in (("u", L.FIELD_U), ("v", L.FIELD_V), ("w", L.FIELD_W), ("p", L.FIELD_P))}
+    t0, i0 = g.time, g.istep
+    th = load.write_checkpoint_async(g, str(tmp_path / "data"))
+    for _ in range(3):          # the fields change while the writer thread works
+        g.step()
+    th.join()
+    assert g.istep == i0 + 3
+    for r in g.ranks:
+        ib, ng, lo1, hi1, _ = load._block_frame(case, r)
+        for k in "uvwp":
+            a = np.zeros(g.shape(r), order="F")
+            tm, it = load.load_one("r", str(tmp_path / "data" / f"fld_b_{ib + 1:03d}_{k}.bin"), ng, lo1, hi1, a)
+            assert it == i0 and abs(tm - t0) <= 1e-14 * max(abs(t0), 1.0)
+            np.testing.assert_array_equal(a[1:-1, 1:-1, 1:-1], ref[(r, k)][1:-1, 1:-1, 1:-1])
+            assert not np.array_equal(a[1:-1, 1:-1, 1:-1], g.download(r, {"u": L.FIELD_U, "v": L.FIELD_V, "w": L.FIELD_W, "p": L.FIELD_P}[k])[1:-1, 1:-1, 1:-1])
+    g.close()
