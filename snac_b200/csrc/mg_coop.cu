@@ -301,7 +301,7 @@ void mg_coop_release(MGCoopState *s) {
 // builds the device tables; nullptr when the path does not apply (boxes coupled across processes, a device without
 // cooperative launches, more than 24 levels)
 MGCoopState *mg_coop_setup(Ctx &ctx, MGSolver &S, const bool coupled[3]) {
-  static const bool off = getenv("SNAC_MG_COOP") && atoi(getenv("SNAC_MG_COOP")) == 0;   // A/B switch: one launch per box, colour and level
+  const bool off = getenv("SNAC_MG_COOP") && atoi(getenv("SNAC_MG_COOP")) == 0;   // A/B switch and test hook: one launch per box, colour and level
   if (off || S.distributed || S.levels.size() > 24 || S.fft_dir == 0 || S.fft_dir == 1) return nullptr;
   for (auto &L : S.levels)
     for (int d = 0; d < 3; ++d)

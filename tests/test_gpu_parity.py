@@ -530,6 +530,14 @@ def test_duct_blocks_without_merging_go_through_the_block_interfaces(tmp_path, m
     _solve_and_compare(tmp_path, "duct", 1, {}, False)
 
 
+@pytest.mark.parametrize("kind,fa", [("channel", 0), ("lshape", 1)])
+def test_general_multigrid_one_launch_per_box_colour_and_level(tmp_path, monkeypatch, kind, fa):
+    """the per-launch form of the general multi-box multigrid (what boxes coupled across processes use) on one GPU, with
+    the cooperative one-launch form switched off: same solver, same answers"""
+    monkeypatch.setenv("SNAC_MG_COOP", "0")
+    _solve_and_compare(tmp_path, kind, fa, {}, False)
+
+
 def test_asynchronous_checkpoint_holds_the_fields_of_its_step(tmp_path):
     """snac_download_async / load.write_checkpoint_async: the files hold the fields as they were when the checkpoint was
     requested, although the time loop went on while they were copied and written."""
