@@ -133,6 +133,10 @@ SNAC_HD void dft(Cx (&v)[R]) {
 #ifndef SNAC_FFT_TP_LONG
 #define SNAC_FFT_TP_LONG 16
 #endif
+#ifndef SNAC_FFT_MINB_FROM
+#define SNAC_FFT_MINB_FROM 256   // shortest transform whose forward kernel is held to SNAC_FFT_MINB_LONG CTAs per SM (64 KB tiles:
+                                 // n = 256 with 32 pencils, n = 512 with 16; Taylor-Green 256^3: forward 3.8 -> 4.5 TB/s)
+#endif
 #ifndef SNAC_FFT_MINB_LONG
 #define SNAC_FFT_MINB_LONG 3
 #endif
@@ -180,10 +184,10 @@ struct Plan {
   static constexpr int TP = tp_of(N);              // pencils per tile
   static constexpr int TPP = R1 < R2 ? R1 : R2;   // threads per pencil
   static constexpr int THREADS = TP * TPP;
-  // CTAs per SM the register allocation of the forward kernel aims at (0: the compiler's choice).  n = 512: three CTAs
+  // CTAs per SM the register allocation of the forward kernel aims at (0: the compiler's choice).  n >= 256: three CTAs
   // of 64 KB; with several processes the stores of a tile cross NVLink and only other CTAs can cover that latency
   // (2 GPUs, channel: forward transform 4.97 -> 3.35 ms per step)
-  static constexpr int MINB_FWD = N >= 512 ? SNAC_FFT_MINB_LONG : 0;
+  static constexpr int MINB_FWD = N >= SNAC_FFT_MINB_FROM ? SNAC_FFT_MINB_LONG : 0;
   static constexpr size_t SMEM = (size_t)M * TP * sizeof(double2);
   SNAC_HD static int loc(int k) { return (k % R1) * S1 + k / R1; }   // where X[k] sits after the two passes
 };
