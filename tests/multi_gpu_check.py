@@ -56,6 +56,11 @@ def main():
             if rank != 0:
                 case = setup_case(tmp[0], fft_axis=fa, impdiff=imp, boussinesq=bou)
         nr = case.world.nrank
+        if nr < world:   # fewer boxes than processes (e.g. the three L-shaped blocks on four GPUs): nothing to own
+            if rank == 0:
+                print(f"[{world} GPUs] {kind} fft_axis={fa} {kw}: {nr} boxes, skipped", flush=True)
+            dist.barrier()
+            continue
         owner = [r % world for r in range(nr)]
         g = Simulation(case, device=local, nproc=world, myproc=rank, rank_owner=owner, tol=1e-12, maxiter=200)
         ini = initial_fields(case, noise=(kind in ("channel", "duct", "lshape")))
