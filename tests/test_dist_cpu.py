@@ -116,8 +116,27 @@ class _FakeSim:
     def download(self, r, field):
         return np.asfortranarray(np.random.default_rng(100 * r + field).standard_normal(self.shape(r)))
 
+    # the asynchronous pair (snac_download_async / snac_download_wait): the array is complete only once its ticket has
+    # been waited for -- a timer fills it 50 ms after the request
+    def download_async(self, r, field):
+        import threading
+        if not hasattr(self, "_events"):
+            self._events = []
+        a = np.full(self.shape(r), np.nan, order="F")
+        ev = threading.Event()
 
-def _ckpt_worker(rank, world, port, rundir, datadir):
+        def land():
+            a[...] = self.download(r, field)
+            ev.set()
+        threading.Timer(0.05, land).start()
+        self._events.append(ev)
+        return a, len(self._events) - 1, (lambda: None)
+
+    def download_wait(self, ticket):
+        assert self._events[ticket].wait(30)
+
+
+def _ckpt_worker(rank, world, port, rundir, datadir, asynchronous=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -127,12 +146,19 @@ def _ckpt_worker(rank, world, port, rundir, datadir):
     from snac_b200.case import setup_case
     case = setup_case(rundir, fft_axis=2)
     sim = _FakeSim(case, [r for r in range(case.world.nrank) if r % world == rank])   # rank <-> GPU as in main.py
-    load.write_checkpoint(sim, datadir)
+    if asynchronous:   # the writer thread of the time loop (main.py): join, then the barrier
+        load.write_checkpoint_async(sim, datadir).join()
+    else:
+        load.write_checkpoint(sim, datadir)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_checkpoint_written_by_two_processes_owning_boxes_of_one_block(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("asynchronous", [False, True])
+def test_checkpoint_written_by_two_processes_owning_boxes_of_one_block(tmp_path, asynchronous):
     """one block of 2 x 1 x 2 boxes, boxes dealt to two processes as `python -m snac_b200.main` under torchrun
     does (rank % nproc): every process writes its sub-arrays of the same fld_b_001_*.bin (src/load.f90:161-187)."""
     import sys
@@ -141,8 +167,8 @@ def test_checkpoint_written_by_two_processes_owning_boxes_of_one_block(tmp_path)
     rundir, datadir = str(tmp_path / "run"), str(tmp_path / "data")
     case = cases.make("channel", rundir, fft_axis=2)
     ctx = mp.get_context("spawn")
-    port = 29650 + os.getpid() % 300
-    ps = [ctx.Process(target=_ckpt_worker, args=(r, 2, port, rundir, datadir)) for r in range(2)]
+    port = 29650 + os.getpid() % 300 + (7 if asynchronous else 0)
+    ps = [ctx.Process(target=_ckpt_worker, args=(r, 2, port, rundir, datadir, asynchronous)) for r in range(2)]
     for p in ps:
         p.start()
     for p in ps:
