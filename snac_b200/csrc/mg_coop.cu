@@ -27,7 +27,10 @@ namespace snac {
 
 namespace {
 
-constexpr int COOP_THREADS = 512, COOP_WARPS = COOP_THREADS / 32;
+#ifndef SNAC_MG_COOP_THREADS
+#define SNAC_MG_COOP_THREADS 512
+#endif
+constexpr int COOP_THREADS = SNAC_MG_COOP_THREADS, COOP_WARPS = COOP_THREADS / 32;
 
 struct CoopLevel {
   int box0, nbox;            // this level's entries of CoopArgs::boxes
@@ -360,7 +363,11 @@ MGCoopState *mg_coop_setup(Ctx &ctx, MGSolver &S, const bool coupled[3]) {
   // the grid is no wider than level 0 needs (a grid-wide barrier costs more the more CTAs take part); all CTAs must be
   // resident at once
   const long want = std::max(1L, (rows0 + 2 * COOP_WARPS - 1) / (2 * COOP_WARPS));   // two rows of level 0 per warp
-  st->grid = (int)std::min<long>(want, (long)sms * std::min(per_sm, 2));
+  // one CTA per SM: a grid-wide barrier costs more the more CTAs take part, and the phases are short (128^3 cavity: 8.0 ms per
+  // step with two CTAs per SM, 6.4 ms with one); SNAC_MG_COOP_GRID: tuning hook, the number of CTAs
+  long cap = sms;
+  if (getenv("SNAC_MG_COOP_GRID")) cap = std::min<long>((long)sms * per_sm, std::max(1, atoi(getenv("SNAC_MG_COOP_GRID"))));
+  st->grid = (int)std::min<long>(want, cap);
   SNAC_CUDA(cudaMallocHost(&st->h_result, 2 * sizeof(double)));
   st->h_result[0] = st->h_result[1] = 0.0;
   return st.release();
