@@ -128,3 +128,42 @@ def test_two_processes_over_peer_memory_against_the_oracle():
                        capture_output=True, text=True, timeout=900)
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_duct_at_full_size_against_the_cpu_restatement(tmp_path):
+    """configs[3] at its full size (512 x 128 x 128 cut into 2 x 2 friend blocks, FFT_AXIS = 1): the transform along the
+    unit-stride axis with its tile staged through shared memory at n = 512, the merged blocks in the direct plane solver
+    and the z-marching kernels on 512 x 64 x 64 boxes, with bench.py's own comparison (the CPU restatement works on the
+    whole rectangle)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import cpu_port
+    from snac_b200.sim import Simulation
+    cpu_port.use_all_cores()
+    case, owner, _, topo = bench.make_case("duct", (512, 128, 128), 1, str(tmp_path))
+    g = Simulation(case, tol=1e-10, maxiter=300)
+    g.set_fields(initial_fields(case, ranks=g.ranks, noise=True))
+    g.init_bc()
+    g.set_dt()
+    c = bench.cpu_sim(case, topo, True, tol=1e-10, maxiter=300)
+    for _ in range(2):
+        c.step(g.dt)
+        g.step()
+    lo0 = np.min([b.lo for b in case.world.boxes], axis=0)
+    ref = [c.get(k) for k in range(4)]
+    I = (slice(1, -1),) * 3
+    vmag = np.sqrt(sum(np.linalg.norm(ref[k][I]) ** 2 for k in range(3)))
+    num = np.zeros(3)
+    for r in g.ranks:
+        b = case.world.boxes[r]
+        o = [int(x) for x in (b.lo - lo0)]
+        sl = tuple(slice(o[d] + 1, o[d] + 1 + int(b.n[d])) for d in range(3))
+        f = g.get_fields(r)
+        for k, key in enumerate("uvw"):
+            num[k] += float(np.sum((f[key][I] - ref[k][sl]) ** 2))
+    for k in range(3):
+        assert np.sqrt(num[k]) <= 1e-8 * max(np.linalg.norm(ref[k][I]), 1e-6 * vmag), (k, np.sqrt(num[k]))
+    divtot, divmax = g.chkdiv()
+    assert divmax < 1e-7
+    assert g.solver_name() == "direct"
+    g.close(); c.close()
