@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(128) tri_factor_kernel(const TriArgs a) {
 // issued a batch of U rows ahead of their use (explicit register double-buffering), so that every thread keeps
 // 2U-3U loads in flight whatever the number of columns -- with few columns (small planes) nothing else hides
 // the memory latency.
-constexpr int TRI_U = 8;
+#ifndef SNAC_TRI_U
+#define SNAC_TRI_U 8
+#endif
+constexpr int TRI_U = SNAC_TRI_U;
 template <bool CYC>
 __global__ void __launch_bounds__(128) tri_solve_kernel(const TriArgs a, const double *__restrict__ b, double *__restrict__ x) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
